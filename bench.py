@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: all-pairs gravity + leapfrog step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-bodies N]
+
+metric  : pairwise interactions/s (fp64), N^2 ordered interactions per force evaluation,
+          one force evaluation per leapfrog step.
+workload: N=1 GPU  -> BASELINE configs[2]: Plummer sphere N=262,144, fast (roofline) kernel.
+          N>1 GPUs -> BASELINE configs[4]: Plummer sphere N=2,097,152, targets partitioned by rank,
+                      NCCL all-gather of the packed positions every step (strong scaling).
+A "step" is one pass of the hot path: half-kick+drift -> force -> half-kick, through the C ABI
+(orb_step_begin / orb_accel / orb_step_kick -- the same kernels orb_step launches, split so the
+force pass can be bracketed by CUDA events on the launching stream).
+
+--impl reference times the reference's own CPU algorithm (the oracle port, oracle/nbody_oracle.c,
+all host threads) on the same workload/metric with a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(REPO, "orbital-physics_b200"), REPO):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "pairwise interactions/sec (fp64)"
+UNIT = "interactions/s"
+FLOP_PER_INTERACTION = 20.0            # BASELINE.json convention
+FP64_NOMINAL_TFLOPS = 37.2             # 148 SMs x 64 lanes x 2 flop x 1.965 GHz
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-bodies", type=int, default=0, help="override the workload size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ensemble", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
+    return ap.parse_args()
+
+
+def workload(args):
+    n = args.n_bodies or (262144 if args.gpus == 1 else 2097152)
+    name = (f"Plummer sphere N={n} all-pairs force + leapfrog step"
+            + ("" if args.gpus == 1 else f", targets partitioned over {args.gpus} GPUs, NCCL all-gather of positions"))
+    return n, name
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_sample(n, cloud, budget_s, nthreads=0):
+    """Time the oracle port (reference algorithm, C, all host threads) on a bounded row sample."""
+    from oracle import load_c_oracle
+    orc = load_c_oracle()
+    threads = orc.max_threads if nthreads <= 0 else nthreads
+    rng = np.random.default_rng(1)
+    probe = rng.choice(n, size=min(n, 64 * threads), replace=False).astype(np.int64)
+    t0 = time.perf_counter()
+    orc.pairwise_sample(cloud["x"], cloud["y"], cloud["z"], cloud["m"], cloud["eps"], cloud["G"], probe, nthreads=threads)
+    rate = len(probe) * (n - 1) / (time.perf_counter() - t0)
+    rows_n = int(max(threads, min(n, rate * budget_s / (n - 1))))
+    rows = rng.choice(n, size=rows_n, replace=False).astype(np.int64)
+    t0 = time.perf_counter()
+    orc.pairwise_sample(cloud["x"], cloud["y"], cloud["z"], cloud["m"], cloud["eps"], cloud["G"], rows, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": rows_n * (n - 1) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{rows_n} of {n} target rows x {n - 1} sources of the same Plummer IC, "
+                      f"oracle/nbody_oracle.c row form (reference rounding sequence), {dt:.1f} s wall",
+            "host_cpus": os.cpu_count()}, rows_n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from core import synthetic
+    n, name = workload(args)
+    cloud = synthetic.plummer(n)
+    from oracle import load_c_oracle
+    orc = load_c_oracle()
+    threads = orc.max_threads
+    rng = np.random.default_rng(1)
+    # calibrate ~3 s of CPU work per step
+    probe = rng.choice(n, size=min(n, 32 * threads), replace=False).astype(np.int64)
+    t0 = time.perf_counter()
+    orc.pairwise_sample(cloud["x"], cloud["y"], cloud["z"], cloud["m"], cloud["eps"], cloud["G"], probe, nthreads=threads)
+    rate = len(probe) * (n - 1) / (time.perf_counter() - t0)
+    per_step = max(1.0, min(3.0, 150.0 / max(1, args.steps + args.warmup)))
+    rows_n = int(max(threads, min(n, rate * per_step / (n - 1))))
+    rows = rng.choice(n, size=rows_n, replace=False).astype(np.int64)
+
+    def one_step():
+        orc.pairwise_sample(cloud["x"], cloud["y"], cloud["z"], cloud["m"], cloud["eps"], cloud["G"], rows,
+                            nthreads=threads)
+
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    value = args.steps * rows_n * (n - 1) / dt
+    sample = (f"each step = {rows_n} of {n} target rows x {n - 1} sources (bounded sample of the force pass), "
+              f"oracle port of core/physics.py:125-159, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "n_bodies": n, "interactions_per_step": "N^2 (extrapolated from the sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- ensemble side measurement
+def ensemble_measure(device, torch, nsys=65536, nbody=16, steps=200):
+    """BASELINE configs[3] on this rank: achieved HBM GB/s (one step per launch) and fused interactions/s."""
+    from core import _native, synthetic
+    e = synthetic.ensemble_fast(nsys, nbody)
+    ens = _native.DeviceEnsemble(nsys, nbody, device, _native.MODE_FAST)
+    ens.set_stream(torch.cuda.current_stream().cuda_stream)
+    ens.set_params(e["dt"], e["eps"], e["G"])
+    ens.upload(*(e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ens.step(20, fused=False)
+    torch.cuda.synchronize()
+    ev0.record(); ens.step(steps, fused=False); ev1.record(); torch.cuda.synchronize()
+    ms_unfused = ev0.elapsed_time(ev1)
+    ens.step(20, fused=True)
+    torch.cuda.synchronize()
+    ev0.record(); ens.step(steps, fused=True); ev1.record(); torch.cuda.synchronize()
+    ms_fused = ev0.elapsed_time(ev1)
+    ens.close()
+    bytes_step = 152.0 * nsys * nbody
+    return {"workload": f"{nsys} independent {nbody}-body systems, one CTA per system",
+            "unfused_gbs": bytes_step * steps / (ms_unfused * 1e-3) / 1e9,
+            "unfused_system_steps_per_s": nsys * steps / (ms_unfused * 1e-3),
+            "fused_interactions_per_s": nsys * nbody * nbody * steps / (ms_fused * 1e-3),
+            "bytes_per_body_step": 152, "steps": steps}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from core import _native, synthetic
+    from core.distributed import ShardedSystem, slab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or _native.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, name = workload(args)
+    if n % world:
+        raise SystemExit(f"n={n} not divisible by world size {world}")
+    cloud = synthetic.plummer(n)
+    stream = torch.cuda.current_stream().cuda_stream
+    lo, hi = slab(n, world, rank)
+
+    if world == 1:
+        dev = _native.DeviceSystem(n, local, _native.MODE_FAST)
+        dev.set_stream(stream)
+        dev.set_params(cloud["dt"], cloud["eps"], cloud["G"])
+        dev.upload(*cloud.arrays())
+        dev.accel()
+        gather = lambda: None
+    else:
+        sh = ShardedSystem(*cloud.arrays(), cloud["dt"], cloud["eps"], cloud["G"], mode=_native.MODE_FAST, device=local)
+        dev = sh.dev
+        gather = sh._all_gather_positions
+    info = dev.force_kernel_info()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    force_ev = []
+
+    def one_step(timed):
+        flush.zero_()                                   # L2 flush between iterations
+        dev.step_begin()
+        gather()
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); dev.accel(); b.record()
+            force_ev.append((a, b))
+        else:
+            dev.accel()
+        dev.step_kick()
+
+    for _ in range(max(3, args.warmup)):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = dev.launch_count()
+    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_ev0.record()
+    for _ in range(args.steps):
+        one_step(True)
+    t_ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = dev.launch_count() - launches0 + args.steps        # + the flush memset per step
+    ms_total = t_ev0.elapsed_time(t_ev1)
+    force_ms = float(np.mean([a.elapsed_time(b) for a, b in force_ev]))
+    if world > 1:
+        t = torch.tensor([ms_total, force_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, force_ms = float(t[0]), float(t[1])
+    value = float(n) * n * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    pin = _native.PinnedBuffer(8 * n + 6 * n)
+    hin = pin.array[: 8 * n].reshape(8, n)
+    hout = pin.array[8 * n:].reshape(6, n)
+    for k, a in enumerate(cloud.arrays()):
+        hin[k] = a
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        dev.upload(*[hin[k] for k in range(8)])          # H2D of this step's inputs
+        dev.step_begin(); gather(); dev.accel(); dev.step_kick()
+        dev.download_state(hout)                           # D2H of the step's result (synchronises)
+
+    dev.accel()
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e = {"value": float(n) * n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * 8 * n + n,
+           "d2h_bytes_per_step": 6 * 8 * n, "steps": e2e_steps,
+           "path": "orb_upload (pinned host SoA) -> orb_step_begin/orb_accel/orb_step_kick -> orb_download_state"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (force pass of the local targets)
+    peak = _native.fp64_peak(local, 1.0)
+    local_interactions = float(hi - lo) * n
+    achieved_tf = FLOP_PER_INTERACTION * local_interactions / (force_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp64", "achieved": achieved_tf, "peak": peak["tflops_mean"], "unit": "TFLOP/s",
+        "frac": achieved_tf / peak["tflops_mean"], "traffic": None,
+        "kernel": info["name"], "grid": info["grid"], "block": info["block"],
+        "kernel_ms": force_ms, "interactions_per_launch": local_interactions,
+        "flop_per_interaction": FLOP_PER_INTERACTION,
+        "peak_source": "measured: orb_fp64_peak DFMA chain on this GPU, mean over 1 s "
+                       f"(burst {peak['tflops_best']:.2f} TF at {peak['sm_clock_mhz']:.0f} MHz); "
+                       "MEASURED_PEAKS.json has no FP64 figure",
+        "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,
+        "algorithmic_hbm_bytes_per_launch": 56 * n,
+        "fp64_instr_per_interaction": 16,
+        "fp64_pipe_util_est": achieved_tf / FLOP_PER_INTERACTION * 16 * 2 / peak["tflops_mean"],
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "n_bodies": n, "mode": "fast", "ic": "Plummer (Aarseth-Henon-Wielen), seed=N",
+                   "interactions_per_step": "N^2", "l2": "flushed between steps (256 MiB memset)",
+                   "parallelism": "1 GPU" if world == 1 else f"target-partition x{world} + all-gather"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cb, _, _ = cpu_sample(n, cloud, args.cpu_seconds)
+        cb["note"] = ("C port of the reference algorithm on all host threads; the reference itself is single-threaded "
+                      "Python at ~5-7 us per pair (BASELINE.md section 2)")
+        line["cpu_baseline"] = cb
+    if world == 1 and not args.no_ensemble:
+        try:
+            line["ensemble"] = ensemble_measure(local, torch)
+        except Exception as exc:      # never lose the headline line over the side measurement
+            line["ensemble"] = {"error": str(exc)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

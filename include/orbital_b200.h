@@ -1,0 +1,180 @@
+/*
+ * orbital_b200.h -- C ABI of liborbital_b200.so (sm_100a).
+ *
+ * The reference (trevormcguire/orbital-physics) is pure Python and has no FFI:
+ * its only seam for the hot path is the Python import surface of
+ * core.engine / core.physics.  This header is the boundary a
+ * drop-in replacement binds instead: plain pointers and sizes, no torch or
+ * NumPy types.  orbital-physics_b200/core/_native.py is the ctypes binding;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Each entry point names the reference code it replaces (file:line relative to
+ * the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 (ORB_OK) or an ORB_ERR_* code; the message for
+ *     the calling thread's last failure is orb_last_error().
+ *   - host arrays are structure-of-arrays fp64, one entry per body.
+ *   - a handle is internally serialised by a mutex: one writer thread calling
+ *     orb_step and any number of reader threads calling orb_download_* is the
+ *     reference app's threading contract (app/app.py:104-115).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ *     with ORB_ERR_NO_DEVICE.
+ */
+#ifndef ORBITAL_B200_H
+#define ORBITAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORB_ABI_VERSION 1
+
+enum orb_status {
+    ORB_OK = 0,
+    ORB_ERR_INVALID = 1,     /* bad argument / state                         */
+    ORB_ERR_CUDA = 2,        /* a CUDA runtime call failed                   */
+    ORB_ERR_NO_DEVICE = 3,   /* no usable CUDA device (no CPU fallback)      */
+    ORB_ERR_OOM = 4
+};
+
+enum orb_mode {
+    /* Bit-faithful: the reference's exact rounding sequence,
+     * ascending-j accumulation, IEEE sqrt/div. Results equal the reference bit for bit. */
+    ORB_MODE_FAITHFUL = 0,
+    /* Roofline kernel: TMA-staged source tiles, rsqrt seed + fp64 polynomial
+     * refinement, register accumulators. Relative acceleration error <= 1e-12. */
+    ORB_MODE_FAST = 1
+};
+
+typedef struct orb_engine orb_engine;       /* one N-body system            */
+typedef struct orb_ensemble orb_ensemble;   /* many independent small ones  */
+
+/* ---- library / device ------------------------------------------------- */
+int orb_abi_version(void);
+const char* orb_last_error(void);
+int orb_device_count(int* count);
+int orb_device_info(int device, char* name, int name_len, int* sm_count,
+                    int* cc_major, int* cc_minor, int64_t* total_mem_bytes);
+/* Pinned host memory for the upload/download staging of large systems. */
+int orb_host_alloc(void** ptr, int64_t bytes);
+int orb_host_free(void* ptr);
+/* Measured FP64 DFMA-chain throughput of `device` (TFLOP/s, 2 flop per DFMA):
+ * the roofline denominator for the force kernel. Runs back-to-back launches for
+ * about `seconds`; best = fastest launch (burst), mean = average over the second
+ * half of the run (sustained, under the power cap); clock from clock64(). */
+int orb_fp64_peak(int device, double seconds, double* tflops_best, double* tflops_mean,
+                  double* sm_clock_mhz);
+
+/* ---- engine lifecycle --------------------------------------------------
+ * Replaces the state held by SimulationEngine / ObjectCollection / Object
+ * (core/engine.py:19-46, core/physics.py:161-191,452-508).
+ * orb_create:         all n bodies are integrated on `device`.
+ * orb_create_sharded: bodies [tgt_lo, tgt_hi) are integrated here, all n act as
+ *                     sources (multi-GPU target partition).     */
+int orb_create(orb_engine** out, int64_t n, int device, int mode);
+int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi,
+                       int device, int mode);
+int orb_destroy(orb_engine* e);
+
+/* SimulationEngine(dt=, softening=) + STANDARD.G (core/engine.py:31-32, core/constants.py:49-58). */
+int orb_set_params(orb_engine* e, double dt, double eps, double G);
+int orb_set_mode(orb_engine* e, int mode);
+/* Device ring of the last `capacity` position snapshots (engine.history, core/engine.py:34,88-92).
+ * 0 disables recording. Resets the ring. */
+int orb_set_history(orb_engine* e, int64_t capacity);
+/* Run on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream. NULL = own stream. */
+int orb_set_stream(orb_engine* e, void* cuda_stream);
+
+/* ---- state transfer ----------------------------------------------------
+ * Upload replaces positions, velocities, masses, radii (Object attributes,
+ * core/physics.py:181-184). vel_is_f32[i] != 0 marks a body whose velocity is a
+ * float32 array in the reference (core/physics.py:184): its velocity is rounded
+ * to float32 after every update and the drift product is formed in float32
+ * (SURVEY.md A.2). NULL = all fp64. Accelerations are NOT touched (the
+ * reference keeps a stale self.acc after external mutation, core/engine.py:85). */
+int orb_upload(orb_engine* e, const double* x, const double* y, const double* z,
+               const double* vx, const double* vy, const double* vz,
+               const double* m, const double* radius, const uint8_t* vel_is_f32);
+int orb_download_state(orb_engine* e, double* x, double* y, double* z,
+                       double* vx, double* vy, double* vz);
+int orb_download_acc(orb_engine* e, double* ax, double* ay, double* az);   /* engine.acc */
+int orb_upload_acc(orb_engine* e, const double* ax, const double* ay, const double* az);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* pairwise_accelerations (core/physics.py:125-159) on the resident positions;
+ * fills the resident acceleration arrays (engine.py:41). Asynchronous. */
+int orb_accel(orb_engine* e);
+/* SimulationEngine.step x nsteps (core/engine.py:65-97): half-kick, drift,
+ * force, half-kick, overlap detection, history append -- one launch sequence
+ * per step under a CUDA graph (one fused single-CTA launch for small n).
+ * Collision *detection* (core/physics.py:517-518) runs on the device; if any
+ * pair overlaps in a step the device halts after that step (before the history
+ * append), *steps_done < nsteps and *n_overlaps > 0: the caller resolves the
+ * contacts with the reference's sequential semantics (core/physics.py:391-422),
+ * re-uploads, calls orb_history_append and resumes. Synchronous on return. */
+int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_overlaps);
+/* Overlapping pairs (i<j) of the halted step, unsorted; *count may exceed cap
+ * (then only cap pairs were stored and the caller must sweep all pairs). */
+int orb_overlap_pairs(orb_engine* e, int64_t* pairs_ij, int64_t cap, int64_t* count);
+/* Split step for sharded engines: begin = half-kick + drift of the local
+ * targets (engine.py:69-75); the caller all-gathers orb_pos4_ptr() slabs;
+ * finish = force + half-kick (engine.py:78-82). Asynchronous. */
+int orb_step_begin(orb_engine* e);
+int orb_step_finish(orb_engine* e);
+/* The second half of orb_step_finish on its own: half-kick (engine.py:81-82) + history append,
+ * so a caller can bracket the force pass (orb_accel) with its own CUDA events. */
+int orb_step_kick(orb_engine* e);
+int orb_synchronize(orb_engine* e);
+
+/* ---- device-resident views (for torch.distributed / CUDA-event timing) -- */
+/* Packed sources: n x {x,y,z,m} fp64 (32 bytes per body). */
+int orb_pos4_ptr(orb_engine* e, void** device_ptr, int64_t* n_bodies);
+int orb_vel_ptr(orb_engine* e, void** device_ptr);   /* 3 x n fp64, SoA */
+int orb_acc_ptr(orb_engine* e, void** device_ptr);   /* 3 x n fp64, SoA */
+/* Name and launch geometry of the force kernel the current mode/size selects. */
+int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, int* block,
+                          int* smem_bytes, int* launches_per_step);
+/* Total kernel launches issued by this handle so far (bench.py gpu_launches). */
+int orb_launch_count(orb_engine* e, int64_t* launches);
+
+/* ---- diagnostics ------------------------------------------------------- */
+/* U = -sum_{i<j} G m_i m_j / sqrt(r^2+eps^2)  (core/physics.py:158; last_potential).
+ * Faithful mode and n <= 4096: lexicographic sequential order (bit-exact). */
+int orb_potential(orb_engine* e, double* U);
+/* K = sum 1/2 m v.v, L = sum r x (m v)  (core/engine.py:104-121), fp64 tree reduction. */
+int orb_energy_angmom(orb_engine* e, double* K, double* L3);
+
+/* ---- history ring (engine.history) -------------------------------------- */
+int orb_history_count(orb_engine* e, int64_t* total_appended);
+/* Append the resident positions now (ctor seed, engine.py:34; post-collision append). */
+int orb_history_append(orb_engine* e);
+/* The most recent min(last_k, stored) snapshots, oldest first: out[k][body][3]. */
+int orb_history_download(orb_engine* e, int64_t last_k, double* out, int64_t* got);
+
+/* ---- batched ensemble: nsys independent systems of nbody bodies ---------
+ * One CTA per system (BASELINE config C3). Arrays are [nsys][nbody] fp64.
+ * Equivalent to nsys separate SimulationEngine instances stepped in lockstep
+ * (core/engine.py:19-46,65-97) without collision handling. */
+int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int mode, int vel_f32);
+int orb_ens_destroy(orb_ensemble* s);
+int orb_ens_set_params(orb_ensemble* s, double dt, double eps, double G);
+int orb_ens_set_stream(orb_ensemble* s, void* cuda_stream);
+int orb_ens_upload(orb_ensemble* s, const double* x, const double* y, const double* z,
+                   const double* vx, const double* vy, const double* vz, const double* m);
+/* fused != 0: all nsteps inside one launch, state in registers/shared memory
+ * (FP64-bound); fused == 0: one launch per step, state round-trips HBM
+ * (104 B per body-step, HBM-bound). Asynchronous. */
+int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused);
+int orb_ens_download(orb_ensemble* s, double* x, double* y, double* z,
+                     double* vx, double* vy, double* vz);
+int orb_ens_energy(orb_ensemble* s, double* E_per_system);
+int orb_ens_synchronize(orb_ensemble* s);
+int orb_ens_launch_count(orb_ensemble* s, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBITAL_B200_H */

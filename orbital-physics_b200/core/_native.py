@@ -1,0 +1,392 @@
+"""ctypes binding of liborbital_b200.so (include/orbital_b200.h).
+
+This is the only place the Python host layer touches native code.  There is no
+CPU fallback: if the shared library is missing, or no CUDA device is present,
+the first compute call raises :class:`NativeError` -- loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+MODE_FAITHFUL = 0
+MODE_FAST = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get(
+    "ORBITAL_B200_LIB", os.path.join(os.path.dirname(_HERE), "csrc", "liborbital_b200.so"))
+
+_f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_i64 = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+_dblp = C.POINTER(C.c_double)
+_intp = C.POINTER(C.c_int)
+
+
+class NativeError(RuntimeError):
+    """A liborbital_b200 call failed (status code + orb_last_error())."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"liborbital_b200 error {code}: {message}")
+        self.code = code
+
+
+# every exported symbol: name -> (restype, argtypes).  tests/test_abi.py checks this
+# table against include/orbital_b200.h.
+SIGNATURES = {
+    "orb_abi_version": (C.c_int, []),
+    "orb_last_error": (C.c_char_p, []),
+    "orb_device_count": (C.c_int, [_intp]),
+    "orb_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, _intp, _intp, _intp, _i64p]),
+    "orb_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_int64]),
+    "orb_host_free": (C.c_int, [_vp]),
+    "orb_fp64_peak": (C.c_int, [C.c_int, C.c_double, _dblp, _dblp, _dblp]),
+    "orb_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int, C.c_int]),
+    "orb_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "orb_destroy": (C.c_int, [_vp]),
+    "orb_set_params": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
+    "orb_set_mode": (C.c_int, [_vp, C.c_int]),
+    "orb_set_history": (C.c_int, [_vp, C.c_int64]),
+    "orb_set_stream": (C.c_int, [_vp, _vp]),
+    "orb_upload": (C.c_int, [_vp] + [_f64] * 8 + [_vp]),
+    "orb_download_state": (C.c_int, [_vp] + [_vp] * 6),
+    "orb_download_acc": (C.c_int, [_vp, _f64, _f64, _f64]),
+    "orb_upload_acc": (C.c_int, [_vp, _f64, _f64, _f64]),
+    "orb_accel": (C.c_int, [_vp]),
+    "orb_step": (C.c_int, [_vp, C.c_int64, _i64p, _i64p]),
+    "orb_overlap_pairs": (C.c_int, [_vp, _i64, C.c_int64, _i64p]),
+    "orb_step_begin": (C.c_int, [_vp]),
+    "orb_step_finish": (C.c_int, [_vp]),
+    "orb_step_kick": (C.c_int, [_vp]),
+    "orb_synchronize": (C.c_int, [_vp]),
+    "orb_pos4_ptr": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
+    "orb_vel_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "orb_acc_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "orb_force_kernel_info": (C.c_int, [_vp, C.c_char_p, C.c_int, _intp, _intp, _intp, _intp]),
+    "orb_launch_count": (C.c_int, [_vp, _i64p]),
+    "orb_potential": (C.c_int, [_vp, _dblp]),
+    "orb_energy_angmom": (C.c_int, [_vp, _dblp, _f64]),
+    "orb_history_count": (C.c_int, [_vp, _i64p]),
+    "orb_history_append": (C.c_int, [_vp]),
+    "orb_history_download": (C.c_int, [_vp, C.c_int64, _vp, _i64p]),
+    "orb_ens_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "orb_ens_destroy": (C.c_int, [_vp]),
+    "orb_ens_set_params": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
+    "orb_ens_set_stream": (C.c_int, [_vp, _vp]),
+    "orb_ens_upload": (C.c_int, [_vp] + [_f64] * 7),
+    "orb_ens_step": (C.c_int, [_vp, C.c_int64, C.c_int]),
+    "orb_ens_download": (C.c_int, [_vp] + [_vp] * 6),
+    "orb_ens_energy": (C.c_int, [_vp, _f64]),
+    "orb_ens_synchronize": (C.c_int, [_vp]),
+    "orb_ens_launch_count": (C.c_int, [_vp, _i64p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load the shared library once; raise NativeError if it is not built."""
+    global _lib
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeError(
+                        -1, f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                            "g.build()'` or `make -C orbital-physics_b200/csrc` (there is no CPU fallback)")
+                L = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                if L.orb_abi_version() != 1:
+                    raise NativeError(-1, "ABI version mismatch between core/_native.py and liborbital_b200.so")
+                _lib = L
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise NativeError(code, (lib().orb_last_error() or b"").decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().orb_device_count(C.byref(n)))
+    return n.value
+
+
+def device_info(device: int = 0) -> dict:
+    name = C.create_string_buffer(256)
+    sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    check(lib().orb_device_info(device, name, 256, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value),
+            "total_mem_bytes": mem.value}
+
+
+def fp64_peak(device: int = 0, seconds: float = 1.0) -> dict:
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    check(lib().orb_fp64_peak(device, seconds, C.byref(a), C.byref(b), C.byref(c)))
+    return {"tflops_best": a.value, "tflops_mean": b.value, "sm_clock_mhz": c.value}
+
+
+def _ptr(a):
+    """void* of a writable contiguous fp64 array, or NULL."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_vp)
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a NumPy fp64 array (orb_host_alloc)."""
+
+    def __init__(self, n_doubles: int):
+        self._p = _vp()
+        check(lib().orb_host_alloc(C.byref(self._p), int(n_doubles) * 8))
+        buf = (C.c_double * int(n_doubles)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.float64)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().orb_host_free(self._p)
+            self._p = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceSystem:
+    """One N-body system resident on a B200: thin object wrapper over the orb_* C ABI.
+
+    State arrays are SoA fp64 NumPy arrays on the host side; nothing is computed
+    on the host.  Used by core.engine.SimulationEngine, by bench.py and by the
+    multi-GPU driver (core.distributed).
+    """
+
+    def __init__(self, n: int, device: int = 0, mode: int = MODE_FAITHFUL, tgt_lo: int | None = None,
+                 tgt_hi: int | None = None):
+        self._h = _vp()
+        self.n = int(n)
+        self.device = int(device)
+        self.mode = int(mode)
+        self.tgt_lo = 0 if tgt_lo is None else int(tgt_lo)
+        self.tgt_hi = self.n if tgt_hi is None else int(tgt_hi)
+        L = lib()
+        if self.tgt_lo == 0 and self.tgt_hi == self.n:
+            check(L.orb_create(C.byref(self._h), self.n, self.device, self.mode))
+        else:
+            check(L.orb_create_sharded(C.byref(self._h), self.n, self.tgt_lo, self.tgt_hi, self.device, self.mode))
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if self._h:
+            lib().orb_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration -----------------------------------------------------
+    def set_params(self, dt: float, eps: float, G: float = 6.67430e-11):
+        check(lib().orb_set_params(self._h, float(dt), float(eps), float(G)))
+
+    def set_mode(self, mode: int):
+        check(lib().orb_set_mode(self._h, int(mode)))
+        self.mode = int(mode)
+
+    def set_history(self, capacity: int):
+        check(lib().orb_set_history(self._h, int(capacity)))
+
+    def set_stream(self, cuda_stream: int | None):
+        check(lib().orb_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+
+    # -- transfers ---------------------------------------------------------
+    def upload(self, x, y, z, vx, vy, vz, m, radius, vel_is_f32=None):
+        arrs = [_c64(a) for a in (x, y, z, vx, vy, vz, m, radius)]
+        for a in arrs:
+            if a.shape != (self.n,):
+                raise ValueError(f"expected arrays of shape ({self.n},), got {a.shape}")
+        flags = None
+        if vel_is_f32 is not None:
+            flags = np.ascontiguousarray(np.broadcast_to(np.asarray(vel_is_f32, dtype=np.uint8), (self.n,)))
+        check(lib().orb_upload(self._h, *arrs, flags.ctypes.data_as(_vp) if flags is not None else None))
+
+    def download_state(self, out=None):
+        """-> dict of x y z vx vy vz (fresh arrays, or views of `out` [6,n])."""
+        if out is None:
+            out = np.empty((6, self.n))
+        check(lib().orb_download_state(self._h, *[_ptr(out[k]) for k in range(6)]))
+        return dict(zip(("x", "y", "z", "vx", "vy", "vz"), out))
+
+    def download_acc(self):
+        a = np.empty((3, self.n))
+        check(lib().orb_download_acc(self._h, a[0], a[1], a[2]))
+        return a
+
+    def upload_acc(self, acc3n):
+        a = _c64(acc3n)
+        check(lib().orb_upload_acc(self._h, a[0], a[1], a[2]))
+
+    # -- hot path ----------------------------------------------------------
+    def accel(self):
+        check(lib().orb_accel(self._h))
+
+    def step(self, nsteps: int = 1):
+        """-> (steps_done, n_overlaps).  steps_done < nsteps iff the device halted on a contact."""
+        done, nov = C.c_int64(0), C.c_int64(0)
+        check(lib().orb_step(self._h, int(nsteps), C.byref(done), C.byref(nov)))
+        return done.value, nov.value
+
+    def overlap_pairs(self, cap: int = 1 << 16):
+        buf = np.empty((cap, 2), dtype=np.int64)
+        cnt = C.c_int64(0)
+        check(lib().orb_overlap_pairs(self._h, buf.reshape(-1), cap, C.byref(cnt)))
+        return buf[: min(cnt.value, cap)].copy(), cnt.value
+
+    def step_begin(self):
+        check(lib().orb_step_begin(self._h))
+
+    def step_finish(self):
+        check(lib().orb_step_finish(self._h))
+
+    def step_kick(self):
+        check(lib().orb_step_kick(self._h))
+
+    def synchronize(self):
+        check(lib().orb_synchronize(self._h))
+
+    # -- device views ------------------------------------------------------
+    def pos4_ptr(self) -> int:
+        p, n = _vp(), C.c_int64()
+        check(lib().orb_pos4_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value
+
+    def vel_ptr(self) -> int:
+        p = _vp()
+        check(lib().orb_vel_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def acc_ptr(self) -> int:
+        p = _vp()
+        check(lib().orb_acc_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def force_kernel_info(self) -> dict:
+        name = C.create_string_buffer(128)
+        g, b, s, l = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().orb_force_kernel_info(self._h, name, 128, C.byref(g), C.byref(b), C.byref(s), C.byref(l)))
+        return {"name": name.value.decode(), "grid": g.value, "block": b.value, "smem": s.value,
+                "launches_per_step": l.value}
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(lib().orb_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # -- diagnostics -------------------------------------------------------
+    def potential(self) -> float:
+        u = C.c_double()
+        check(lib().orb_potential(self._h, C.byref(u)))
+        return u.value
+
+    def energy_angmom(self):
+        k = C.c_double()
+        L3 = np.empty(3)
+        check(lib().orb_energy_angmom(self._h, C.byref(k), L3))
+        return k.value, L3
+
+    # -- history -----------------------------------------------------------
+    def history_count(self) -> int:
+        v = C.c_int64()
+        check(lib().orb_history_count(self._h, C.byref(v)))
+        return v.value
+
+    def history_append(self):
+        check(lib().orb_history_append(self._h))
+
+    def history_download(self, last_k: int) -> np.ndarray:
+        """-> [k, n, 3] oldest first."""
+        last_k = int(last_k)
+        out = np.empty((max(last_k, 0), self.n, 3))
+        got = C.c_int64(0)
+        check(lib().orb_history_download(self._h, last_k, _ptr(out.reshape(-1)) if last_k > 0 else None, C.byref(got)))
+        return out[: got.value]
+
+
+class DeviceEnsemble:
+    """nsys independent systems of nbody bodies, one CTA per system (orb_ens_*)."""
+
+    def __init__(self, nsys: int, nbody: int, device: int = 0, mode: int = MODE_FAST, vel_f32: bool = False):
+        self._h = _vp()
+        self.nsys, self.nbody, self.device, self.mode = int(nsys), int(nbody), int(device), int(mode)
+        check(lib().orb_ens_create(C.byref(self._h), self.nsys, self.nbody, self.device, self.mode, int(bool(vel_f32))))
+
+    def close(self):
+        if self._h:
+            lib().orb_ens_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, dt, eps, G=6.67430e-11):
+        check(lib().orb_ens_set_params(self._h, float(dt), float(eps), float(G)))
+
+    def set_stream(self, cuda_stream):
+        check(lib().orb_ens_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+
+    def upload(self, x, y, z, vx, vy, vz, m):
+        arrs = [_c64(a) for a in (x, y, z, vx, vy, vz, m)]
+        for a in arrs:
+            if a.shape != (self.nsys, self.nbody):
+                raise ValueError(f"expected shape ({self.nsys},{self.nbody}), got {a.shape}")
+        check(lib().orb_ens_upload(self._h, *[a.reshape(-1) for a in arrs]))
+
+    def step(self, nsteps: int = 1, fused: bool = True):
+        check(lib().orb_ens_step(self._h, int(nsteps), int(bool(fused))))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty((6, self.nsys, self.nbody))
+        check(lib().orb_ens_download(self._h, *[_ptr(out[k].reshape(-1)) for k in range(6)]))
+        return dict(zip(("x", "y", "z", "vx", "vy", "vz"), out))
+
+    def energy(self):
+        E = np.empty(self.nsys)
+        check(lib().orb_ens_energy(self._h, E))
+        return E
+
+    def synchronize(self):
+        check(lib().orb_ens_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(lib().orb_ens_launch_count(self._h, C.byref(v)))
+        return v.value

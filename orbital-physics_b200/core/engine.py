@@ -1,0 +1,513 @@
+"""SimulationEngine: the kick-drift-kick leapfrog loop, device resident.
+
+Drop-in for the reference's core/engine.py (same constructor, attributes and
+methods; `run_simulation` prints the same diagnostics).  The state of the bound
+`ObjectCollection` lives on the GPU as structure-of-arrays fp64 buffers; one
+`step()` is one launch sequence through the C ABI (core/_native.py):
+
+    half-kick + drift  ->  all-pairs force (+ fused overlap detection)
+                       ->  half-kick + history-ring append
+
+and `run(k)` keeps all k steps on the device (CUDA graph / fused single-CTA
+kernel).  The Python `Object`s are lazy mirrors: the first read after a step
+pulls the state once; a write makes the host copy authoritative and it is
+re-uploaded before the next step.  Contacts are detected on the device and
+resolved on the host with the reference's sequential semantics.
+
+Reference behaviour kept on purpose: `max_hist=-1` keeps only the
+latest history point; `cache=True` by default appends a JSONL frame every
+`cache_every_n` steps (frame time lags its positions by one dt); accelerations
+are *not* recomputed after a collision or an external mutation.
+"""
+from __future__ import annotations
+
+import json
+import os
+import threading
+from collections.abc import Mapping
+
+import numpy as np
+
+from core import _native
+from core.constants import STANDARD
+from core.physics import Coordinates, ObjectCollection, default_device, select_mode
+
+_RING_BYTES = int(os.environ.get("ORBITAL_B200_HISTORY_BYTES", str(256 << 20)))
+_HOST_DIAG_MAX = 4096      # up to this many bodies diagnostics use the reference's NumPy expressions
+
+
+class _HistoryView(Mapping):
+    """`engine.history`: uuid -> list of [x, y, z], materialised lazily from the device ring."""
+
+    def __init__(self, engine: "SimulationEngine"):
+        self._e = engine
+        self._override = {}
+
+    def __getitem__(self, uuid):
+        if uuid in self._override:
+            return self._override[uuid]
+        return self._e._history_list(uuid, 0)
+
+    def __setitem__(self, uuid, value):
+        self._override[uuid] = value
+
+    def __iter__(self):
+        return iter(self._e._uuids)
+
+    def __len__(self):
+        return len(self._e._uuids)
+
+    def __repr__(self):
+        return f"<history of {len(self)} bodies x {self._e._hist_len()} points>"
+
+
+class SimulationEngine:
+    """
+    Engine to advance the orbital simulation forward in time.
+
+    Attributes:
+        objects (ObjectCollection): The collection of objects in the simulation.
+        dt (float): Time step (in seconds).
+        restitution (float): Coefficient of restitution for collisions (0 to 1).
+        softening (float): Softening length to avoid singularities (in meters).
+        history (mapping): uuid -> positions of that object at each recorded step.
+
+    B200-specific keyword-only options (defaults reproduce the reference):
+        mode:   "auto" | "faithful" | "fast"  (env ORBITAL_B200_MODE)
+        device: CUDA device index             (env ORBITAL_B200_DEVICE / LOCAL_RANK)
+    """
+
+    def __init__(self, objects: ObjectCollection, dt: float = 1.0, softening: float = 0.0,
+                 restitution: float = 1.0, max_hist: int = -1, cache: bool = True,
+                 cache_fp: str = "history.jsonl", cache_every_n: int = 300, *, mode=None, device=None):
+        self._lock = threading.RLock()
+        self.objects = objects
+        self.dt = float(dt)
+        self.softening = float(softening)
+        self.restitution = float(restitution)
+        self.max_hist = max_hist
+        self.cache = cache
+        if cache_fp and not cache_fp.endswith(".jsonl"):
+            raise ValueError("cache_fp must end with .jsonl")
+        self.cache_fp = cache_fp
+        self._mode_req = mode
+        self._device = default_device() if device is None else int(device)
+        self._G = STANDARD.G       # the reference never forwards unit_profile (engine.py:41,78)
+
+        self._dev = None
+        self._bound = []
+        self._uuids = []
+        self._index = {}
+        self._snap = None
+        self._device_ahead = False
+        self._host_exposed = False
+        self._host_dirty = False
+        self._force_version = 0
+        self._acc_cache = (None, None)
+        self._U_cache = (None, None)
+        self._params = None
+        self._hist_chunks = []
+        self._hist_drained = 0
+        self._hist_total = 0
+        self._hist_cache = (None, None)
+        self._hist_legacy = {}
+        self._history_view = _HistoryView(self)
+
+        with self._lock:
+            self._bind(initial=True)           # upload + initial accelerations (engine.py:41)
+        self.time_elapsed = 0.
+        self.step_idx = 0
+        self.cache_every_n = cache_every_n if self.cache else 0
+
+    # ------------------------------------------------------------------ binding
+    def _gather(self):
+        objs = self.objects.objects
+        n = len(objs)
+        pos = np.empty((3, n))
+        vel = np.empty((3, n))
+        m = np.empty(n)
+        rad = np.empty(n)
+        f32 = np.zeros(n, dtype=np.uint8)
+        for i, o in enumerate(objs):
+            c = o._coordinates
+            pos[0, i], pos[1, i], pos[2, i] = c.x, c.y, c.z
+            v = o._velocity
+            if not isinstance(v, np.ndarray):
+                v = np.asarray(v, dtype=np.float64)
+            vel[0, i], vel[1, i], vel[2, i] = v[0], v[1], v[2]
+            f32[i] = v.dtype == np.float32
+            m[i] = o._mass
+            rad[i] = o._radius
+        return {"pos": pos, "vel": vel, "m": m, "radius": rad, "f32": f32}
+
+    def _upload(self, g):
+        self._dev.upload(g["pos"][0], g["pos"][1], g["pos"][2], g["vel"][0], g["vel"][1], g["vel"][2],
+                         g["m"], g["radius"], g["f32"])
+        self._snap = g
+
+    def _sync_params(self):
+        p = (float(self.dt), float(self.softening), float(self._G))
+        if p != self._params:
+            self._dev.set_params(*p)
+            self._params = p
+
+    def _hist_limit(self):
+        """None = unbounded, else the number of points the reference's pop(0) logic retains."""
+        return None if self.max_hist is None else max(1, int(self.max_hist))
+
+    def _bind(self, initial: bool):
+        objs = list(self.objects.objects)
+        n = len(objs)
+        old_acc = None
+        if not initial:
+            old_acc = self.acc                              # uuid -> array, from the old binding
+            for u in self._uuids:                           # keep what was recorded so far
+                self._hist_legacy[u] = self._history_list(u, 0)
+        if self._dev is not None:
+            self._dev.close()
+            self._dev = None
+        for o in self._bound:
+            if o._engine is self:
+                o._engine = None
+        self._bound = objs
+        self._uuids = [o.uuid for o in objs]
+        self._index = {u: i for i, u in enumerate(self._uuids)}
+        self._hist_chunks, self._hist_drained, self._hist_total = [], 0, 0
+        self._hist_cache = (None, None)
+        self._params = None
+        if n == 0:
+            self._snap = None
+            self._acc_cache = (self._force_version, {})
+            self._U_cache = (self._force_version, 0.0)
+            return
+        self._dev = _native.DeviceSystem(n, self._device, select_mode(n, self._mode_req))
+        self._sync_params()
+        limit = self._hist_limit()
+        per_snapshot = 24 * n
+        cap_max = max(1, _RING_BYTES // per_snapshot)
+        self._ring_cap = limit if (limit is not None and limit <= cap_max) else cap_max
+        self._drain_mode = limit is None or limit > cap_max
+        self._dev.set_history(self._ring_cap)
+        self._upload(self._gather())
+        for o in objs:
+            o._engine = self
+        self._device_ahead = self._host_exposed = self._host_dirty = False
+        if initial:
+            self._dev.accel()                               # engine.py:41
+            self._force_version += 1
+            self._dev.history_append()                      # engine.py:34 seed point
+            self._hist_total = 1
+        else:
+            a = np.array([old_acc[u] for u in self._uuids]).T   # KeyError for late-added bodies, as the reference
+            self._dev.upload_acc(np.ascontiguousarray(a))
+            self._acc_cache = (self._force_version, {u: old_acc[u] for u in self._uuids})
+
+    # ------------------------------------------------------------ lazy mirroring
+    def _host_read(self):
+        with self._lock:
+            if self._device_ahead:
+                self._pull()
+            self._host_exposed = True
+
+    def _host_write(self):
+        with self._lock:
+            if self._device_ahead:
+                self._pull()
+            self._host_dirty = True
+
+    def _pull(self):
+        """Device -> host mirrors (one transfer)."""
+        st = self._dev.download_state()
+        x, y, z, vx, vy, vz = (st[k] for k in ("x", "y", "z", "vx", "vy", "vz"))
+        for i, o in enumerate(self._bound):
+            o._coordinates = Coordinates(x=x[i], y=y[i], z=z[i])     # np.float64 members, like from_iterable
+            v = o._velocity
+            if isinstance(v, np.ndarray) and v.shape == (3,) and v.dtype in (np.float32, np.float64):
+                v[0], v[1], v[2] = vx[i], vy[i], vz[i]                # in place: dtype and identity kept
+            else:
+                o._velocity = np.array([vx[i], vy[i], vz[i]])
+        s = self._snap
+        s["pos"] = np.stack([x, y, z])
+        s["vel"] = np.stack([vx, vy, vz])
+        self._device_ahead = False
+
+    def _push_if_needed(self):
+        """Host -> device if the host copy may have been modified since the last sync."""
+        objs = self.objects.objects
+        if len(objs) != len(self._bound) or any(a is not b for a, b in zip(objs, self._bound)):
+            if self._device_ahead:
+                self._pull()
+            self._bind(initial=False)
+            return
+        if self._dev is None:
+            return
+        self._sync_params()
+        if not (self._host_exposed or self._host_dirty):
+            return
+        g = self._gather()
+        s = self._snap
+        same = all(np.array_equal(g[k], s[k]) for k in ("pos", "vel", "m", "radius", "f32"))
+        if not same:
+            if len(self._bound) <= _HOST_DIAG_MAX:
+                self._potential()        # U belongs to the last force build: evaluate before positions change
+            self._upload(g)
+        self._host_exposed = self._host_dirty = False
+
+    # ------------------------------------------------------------------ history
+    def _hist_len(self):
+        limit = self._hist_limit()
+        return self._hist_total if limit is None else min(limit, self._hist_total)
+
+    def _drain(self):
+        new = self._hist_total - self._hist_drained
+        if new > 0:
+            self._hist_chunks.append(self._dev.history_download(new))
+            self._hist_drained = self._hist_total
+            limit = self._hist_limit()
+            if limit is not None:
+                tot = sum(c.shape[0] for c in self._hist_chunks)
+                while tot - self._hist_chunks[0].shape[0] >= limit:
+                    tot -= self._hist_chunks.pop(0).shape[0]
+
+    def _history_array(self):
+        """[T, n, 3] of the retained points, oldest first (cached until the next append)."""
+        with self._lock:
+            key, arr = self._hist_cache
+            if key == self._hist_total and arr is not None:
+                return arr
+            if self._dev is None:
+                arr = np.empty((0, 0, 3))
+            elif self._drain_mode:
+                self._drain()
+                arr = np.concatenate(self._hist_chunks, axis=0) if self._hist_chunks else np.empty((0, len(self._bound), 3))
+                limit = self._hist_limit()
+                if limit is not None:
+                    arr = arr[-limit:]
+            else:
+                arr = self._dev.history_download(self._hist_len())
+            self._hist_cache = (self._hist_total, arr)
+            return arr
+
+    def _history_list(self, uuid, limit):
+        legacy = self._hist_legacy.get(uuid, [])
+        if uuid not in self._index:
+            if legacy:
+                return legacy[-limit:] if limit > 0 else legacy
+            raise KeyError(uuid)
+        arr = self._history_array()
+        col = arr[:, self._index[uuid], :]
+        if legacy:
+            pts = legacy + col.tolist()
+            cap = self._hist_limit()
+            if cap is not None:
+                pts = pts[-cap:]
+            return pts[-limit:] if limit > 0 else pts
+        if limit > 0:
+            col = col[-limit:]
+        return col.tolist()
+
+    @property
+    def history(self):
+        return self._history_view
+
+    @history.setter
+    def history(self, value):
+        self._history_view._override = dict(value)
+
+    def named_history(self, limit: int = 0):
+        """Return history with object names as keys instead of UUIDs."""
+        with self._lock:
+            out = {}
+            for obj in self.objects:
+                if obj.uuid in self._history_view._override:
+                    pts = self._history_view._override[obj.uuid]
+                    out[obj.name] = pts[-limit:] if limit > 0 else pts
+                else:
+                    out[obj.name] = self._history_list(obj.uuid, limit)
+            return out
+
+    # --------------------------------------------------------------- force state
+    @property
+    def acc(self):
+        """uuid -> acceleration (np.ndarray(3)) from the last force build."""
+        with self._lock:
+            ver, cached = self._acc_cache
+            if ver == self._force_version and cached is not None:
+                return cached
+            a = self._dev.download_acc() if self._dev is not None else np.empty((3, 0))
+            out = {u: np.array([a[0, i], a[1, i], a[2, i]]) for i, u in enumerate(self._uuids)}
+            self._acc_cache = (self._force_version, out)
+            return out
+
+    @acc.setter
+    def acc(self, value):
+        with self._lock:
+            a = np.array([np.asarray(value[u], dtype=np.float64) for u in self._uuids]).T
+            self._dev.upload_acc(np.ascontiguousarray(a))
+            self._acc_cache = (self._force_version, dict(value))
+
+    def _potential(self):
+        ver, U = self._U_cache
+        if ver == self._force_version and U is not None:
+            return U
+        U = np.float64(self._dev.potential()) if (self._dev is not None and len(self._bound) > 1) else 0.0
+        self._U_cache = (self._force_version, U)
+        return U
+
+    @property
+    def last_potential(self):
+        """Total (softened) potential energy at the last force build (computed on first use)."""
+        with self._lock:
+            return self._potential()
+
+    @last_potential.setter
+    def last_potential(self, value):
+        with self._lock:
+            self._U_cache = (self._force_version, value)
+
+    # ------------------------------------------------------------------- stepping
+    def _resolve_contacts(self):
+        """Device halted on overlapping pairs: apply the reference's sweep to them on the host."""
+        n = len(self._bound)
+        if n <= _HOST_DIAG_MAX:
+            self._potential()                       # U of this force build, before push-out moves bodies
+        pairs, count = self._dev.overlap_pairs()
+        self._pull()
+        if count > len(pairs):                      # list overflowed: fall back to the full sweep
+            self.objects.handle_collisions(restitution=self.restitution)
+        else:
+            self.objects.resolve_contacts(pairs, restitution=self.restitution)
+        g = self._gather()
+        self._upload(g)
+        self._host_exposed = self._host_dirty = False
+        self._dev.history_append()                  # engine.py:88-92 runs after the collision sweep
+
+    def _advance(self, nsteps: int):
+        """nsteps complete steps (engine.py:69-92), all on the device unless a contact halts it."""
+        self._push_if_needed()
+        if self._dev is None:
+            return
+        left = int(nsteps)
+        while left > 0:
+            chunk = left
+            if self._drain_mode:
+                room = self._ring_cap - (self._hist_total - self._hist_drained)
+                if room <= 0:
+                    self._drain()
+                    room = self._ring_cap
+                chunk = min(chunk, room)
+            done, overlaps = self._dev.step(chunk)
+            self._device_ahead = True
+            self._force_version += done
+            self._hist_total += done
+            left -= done
+            if overlaps > 0:
+                self._resolve_contacts()
+            elif done < chunk:
+                raise RuntimeError("device stopped early without reporting a contact")
+
+    def _tick(self):
+        """Book-keeping after one step (engine.py:94-97)."""
+        if self.cache and ((self.step_idx % self.cache_every_n) == 0):
+            self.save_frame()
+        self.step_idx += 1
+        self.time_elapsed += self.dt
+
+    def step(self):
+        with self._lock:
+            self._advance(1)
+            self._tick()
+
+    def run(self, steps: int):
+        """`steps` leapfrog steps; the device runs whole stretches between JSONL frames."""
+        with self._lock:
+            left = int(steps)
+            while left > 0:
+                k = left
+                if self.cache and self.cache_every_n > 0:
+                    k = min(k, (-self.step_idx) % self.cache_every_n + 1)   # stop right after a frame step
+                elif self.cache:
+                    k = 1                                                     # modulo by zero, as the reference
+                self._advance(k)
+                for _ in range(k - 1):                                        # no frame due inside the stretch
+                    self.step_idx += 1
+                    self.time_elapsed += self.dt
+                self._tick()
+                left -= k
+
+    def save_frame(self):
+        """Append the current state to the JSONL cache (same schema as the reference, engine.py:48-57)."""
+        state = {
+            "time_elapsed": self.time_elapsed,
+            "objects": self.objects.to_dict(),
+            "history": self.named_history(limit=1),
+        }
+        with open(self.cache_fp, "a") as f:
+            json.dump(state, f)
+            f.write('\n')
+
+    # ---------------------------------------------------------------- diagnostics
+    def total_energy(self):
+        with self._lock:
+            if len(self._bound) > _HOST_DIAG_MAX:
+                self._push_if_needed()
+                K, _ = self._dev.energy_angmom()
+                return K + self.last_potential
+            K = 0.0
+            for obj in self.objects:
+                v2 = float(obj.velocity @ obj.velocity)
+                K += 0.5 * obj.mass * v2
+            return K + self.last_potential
+
+    def angular_momentum(self):
+        with self._lock:
+            if len(self._bound) > _HOST_DIAG_MAX:
+                self._push_if_needed()
+                return self._dev.energy_angmom()[1]
+            L = np.zeros(3)
+            for obj in self.objects:
+                L += np.cross(obj.position(), obj.mass * obj.velocity)
+            return L
+
+    # ---------------------------------------------------------------------- misc
+    def synchronize(self):
+        with self._lock:
+            if self._dev is not None:
+                self._dev.synchronize()
+
+    def kernel_info(self) -> dict:
+        with self._lock:
+            return self._dev.force_kernel_info()
+
+    def close(self):
+        with self._lock:
+            if self._device_ahead:
+                self._pull()
+            for o in self._bound:
+                if o._engine is self:
+                    o._engine = None
+            if self._dev is not None:
+                self._dev.close()
+                self._dev = None
+
+
+def run_simulation(engine: SimulationEngine, steps: int, print_every: int = 100):
+    """Step `steps` times, printing relative energy / angular-momentum drift every `print_every` steps
+    (at s = 0, print_every, 2*print_every, ... counted before the increment, as the reference)."""
+    E0 = engine.total_energy()
+    L0 = engine.angular_momentum()
+    s = 0
+    while s < steps:
+        # the reference evaluates E, L after the step whose index is a multiple of print_every
+        nxt = s if s % print_every == 0 else s + (print_every - s % print_every)
+        k = min(steps, nxt + 1) - s
+        if k > 1:
+            engine.run(k - 1)
+        engine.step()
+        s += k
+        if (s - 1) % print_every == 0:
+            E = engine.total_energy()
+            L = engine.angular_momentum()
+            dE = (E - E0) / abs(E0)
+            dL = np.linalg.norm(L - L0) / (np.linalg.norm(L0) + 1e-30)
+            print(f"step {s - 1}: ΔE={dE:.3e}, ΔL={dL:.3e}")

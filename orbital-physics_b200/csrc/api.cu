@@ -1,0 +1,795 @@
+// api.cu -- C ABI of liborbital_b200.so (include/orbital_b200.h): handle
+// lifetime, host<->device staging, step orchestration (CUDA graph / fused
+// single-CTA kernel), history ring, diagnostics.  No CPU compute path exists:
+// every entry point that computes needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/orbital_b200.h"
+#include "ensemble.h"
+#include "kernels.h"
+
+using namespace orb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    const int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? ORB_ERR_NO_DEVICE
+                     : (e == cudaErrorMemoryAllocation ? ORB_ERR_OOM : ORB_ERR_CUDA);
+    cudaGetLastError();   // clear sticky-free errors
+    return fail(code, buf);
+}
+
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
+    } while (0)
+
+__global__ void ctl_reset_kernel(Ctl* ctl, int reset_hist) {
+    ctl->steps_done = 0;
+    ctl->halted = 0;
+    ctl->overlap_count = 0;
+    ctl->overlap_overflow = 0;
+    if (reset_hist) ctl->hist_count = 0;
+}
+
+}  // namespace
+
+struct orb_engine {
+    std::mutex mu;
+    int device = 0;
+    int mode = ORB_MODE_FAITHFUL;
+    int sm_count = 148;
+    bool sharded = false;
+    DeviceState s;
+    StepParams p{};
+    FastPlan plan;
+    bool plan_valid = false;
+    bool detect = false;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    double* d_stage = nullptr;       // 4 x n staging for SoA <-> packed conversion
+    double* d_diag = nullptr;        // 8 doubles
+    double* h_diag = nullptr;        // pinned
+    Ctl* h_ctl = nullptr;            // pinned
+    cudaGraphExec_t graph1 = nullptr;   // one step
+    cudaGraphExec_t graphK = nullptr;   // kGraphSteps steps
+    int kernels_per_step = 0;
+    long long launches = 0;
+    bool have_state = false;
+};
+
+namespace {
+
+constexpr int kGraphSteps = 16;
+
+void drop_graphs(orb_engine* e) {
+    if (e->graph1) { cudaGraphExecDestroy(e->graph1); e->graph1 = nullptr; }
+    if (e->graphK) { cudaGraphExecDestroy(e->graphK); e->graphK = nullptr; }
+}
+
+bool use_tiny(const orb_engine* e) {
+    return e->mode == ORB_MODE_FAITHFUL && !e->sharded && e->s.n <= kTinyMax;
+}
+
+int ensure_plan(orb_engine* e) {
+    if (e->mode == ORB_MODE_FAST && !e->plan_valid) {
+        e->plan = plan_fast(e->s.tgt_hi - e->s.tgt_lo, e->s.n, e->sm_count);
+        const long long need = e->plan.slabs > 1 ? (long long)e->plan.slabs * 3 * (e->s.tgt_hi - e->s.tgt_lo) : 0;
+        if (need > e->s.scratch_elems) {
+            if (e->s.scratch) cudaFree(e->s.scratch);
+            e->s.scratch = nullptr;
+            e->s.scratch_elems = 0;
+            CU(cudaMalloc(&e->s.scratch, sizeof(double) * need));
+            e->s.scratch_elems = need;
+        }
+        e->plan_valid = true;
+    }
+    return ORB_OK;
+}
+
+// one force evaluation on the resident positions (physics.py:125-159)
+int enqueue_force(orb_engine* e, bool detect, int* launches) {
+    if (e->mode == ORB_MODE_FAST) {
+        int rc = ensure_plan(e);
+        if (rc) return rc;
+        CU(launch_force_fast(e->s, e->p, e->plan, detect, e->stream, launches));
+    } else {
+        CU(launch_force_faithful(e->s, e->p, detect, e->stream, launches));
+    }
+    return ORB_OK;
+}
+
+// one full leapfrog step as separate kernels (engine.py:65-97)
+int enqueue_step(orb_engine* e, int* launches) {
+    CU(launch_kick_drift(e->s, e->p, e->stream));
+    ++*launches;
+    int rc = enqueue_force(e, e->detect, launches);
+    if (rc) return rc;
+    CU(launch_kick_hist(e->s, e->p, e->stream));
+    CU(launch_advance(e->s, e->stream));
+    *launches += 2;
+    return ORB_OK;
+}
+
+int build_graph(orb_engine* e, int steps, cudaGraphExec_t* out) {
+    int rc = ensure_plan(e);   // allocations must happen outside capture
+    if (rc) return rc;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int launches = 0;
+    for (int k = 0; k < steps && rc == ORB_OK; ++k) rc = enqueue_step(e, &launches);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+    ce = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+    e->kernels_per_step = launches / steps;
+    return ORB_OK;
+}
+
+int alloc_engine(orb_engine* e) {
+    const long long n = e->s.n;
+    CU(cudaMalloc(&e->s.pos4, sizeof(double4) * n));
+    CU(cudaMalloc(&e->s.vel, sizeof(double) * 3 * n));
+    CU(cudaMalloc(&e->s.acc, sizeof(double) * 3 * n));
+    CU(cudaMalloc(&e->s.radius, sizeof(double) * n));
+    CU(cudaMalloc(&e->s.vf32, n));
+    CU(cudaMalloc(&e->s.ctl, sizeof(Ctl)));
+    CU(cudaMalloc(&e->s.pairs, sizeof(long long) * 2 * kOverlapCap));
+    CU(cudaMalloc(&e->s.reduce_buf, sizeof(double) * 4 * ((n + 255) / 256 + 1)));
+    CU(cudaMalloc(&e->d_stage, sizeof(double) * 4 * n));
+    CU(cudaMalloc(&e->d_diag, sizeof(double) * 8));
+    CU(cudaMallocHost(&e->h_diag, sizeof(double) * 8));
+    CU(cudaMallocHost(&e->h_ctl, sizeof(Ctl)));
+    CU(cudaMemset(e->s.vel, 0, sizeof(double) * 3 * n));
+    CU(cudaMemset(e->s.acc, 0, sizeof(double) * 3 * n));
+    CU(cudaMemset(e->s.ctl, 0, sizeof(Ctl)));
+    CU(cudaMemset(e->s.vf32, 0, n));
+    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    return ORB_OK;
+}
+
+void free_engine(orb_engine* e) {
+    drop_graphs(e);
+    cudaFree(e->s.pos4); cudaFree(e->s.vel); cudaFree(e->s.acc); cudaFree(e->s.radius); cudaFree(e->s.vf32);
+    cudaFree(e->s.ctl); cudaFree(e->s.pairs); cudaFree(e->s.hist); cudaFree(e->s.scratch);
+    cudaFree(e->s.reduce_buf); cudaFree(e->d_stage); cudaFree(e->d_diag);
+    if (e->h_diag) cudaFreeHost(e->h_diag);
+    if (e->h_ctl) cudaFreeHost(e->h_ctl);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+}
+
+int select_device(int device) {
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(ORB_ERR_NO_DEVICE,
+                    "no CUDA device available: liborbital_b200 has no CPU fallback (cudaGetDeviceCount: " +
+                        std::string(ce == cudaSuccess ? "0 devices" : cudaGetErrorString(ce)) + ")");
+    }
+    if (device < 0 || device >= count) return fail(ORB_ERR_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    return ORB_OK;
+}
+
+#define LOCK(e)                                                  \
+    if (!(e)) return fail(ORB_ERR_INVALID, "null handle");        \
+    std::lock_guard<std::mutex> _lk((e)->mu);                     \
+    CU(cudaSetDevice((e)->device))
+
+}  // namespace
+
+extern "C" {
+
+int orb_abi_version(void) { return ORB_ABI_VERSION; }
+
+const char* orb_last_error(void) { return g_err.c_str(); }
+
+int orb_device_count(int* count) {
+    if (!count) return fail(ORB_ERR_INVALID, "null argument");
+    int c = 0;
+    cudaError_t ce = cudaGetDeviceCount(&c);
+    if (ce != cudaSuccess) { cudaGetLastError(); c = 0; }
+    *count = c;
+    return ORB_OK;
+}
+
+int orb_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
+                    int64_t* total_mem_bytes) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem_bytes) *total_mem_bytes = (int64_t)prop.totalGlobalMem;
+    return ORB_OK;
+}
+
+int orb_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(ORB_ERR_INVALID, "bad argument");
+    CU(cudaMallocHost(ptr, (size_t)bytes));
+    return ORB_OK;
+}
+
+int orb_host_free(void* ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return ORB_OK;
+}
+
+int orb_fp64_peak(int device, double seconds, double* tflops_best, double* tflops_mean, double* sm_clock_mhz) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    double a = 0, b = 0, c = 0;
+    CU(run_fp64_peak(device, seconds, &a, &b, &c));
+    if (tflops_best) *tflops_best = a;
+    if (tflops_mean) *tflops_mean = b;
+    if (sm_clock_mhz) *sm_clock_mhz = c;
+    return ORB_OK;
+}
+
+int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi, int device, int mode) {
+    if (!out) return fail(ORB_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (n <= 0) return fail(ORB_ERR_INVALID, "n must be positive");
+    if (tgt_lo < 0 || tgt_hi > n || tgt_lo >= tgt_hi) return fail(ORB_ERR_INVALID, "bad target range");
+    if (mode != ORB_MODE_FAITHFUL && mode != ORB_MODE_FAST) return fail(ORB_ERR_INVALID, "bad mode");
+    int rc = select_device(device);
+    if (rc) return rc;
+    orb_engine* e = new orb_engine();
+    e->device = device;
+    e->mode = mode;
+    e->s.n = n;
+    e->s.tgt_lo = tgt_lo;
+    e->s.tgt_hi = tgt_hi;
+    e->sharded = !(tgt_lo == 0 && tgt_hi == n);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete e;
+        return fail(ORB_ERR_NO_DEVICE, "liborbital_b200 is built for sm_100a only; device is older");
+    }
+    e->p.dt = 1.0; e->p.h = 0.5; e->p.dt32 = 1.0f; e->p.eps2 = 0.0; e->p.G = 6.67430e-11;
+    e->p.rmax1 = e->p.rmax2 = 0.0; e->p.rmax1_idx = -1; e->p.detect = 0;
+    rc = alloc_engine(e);
+    if (rc) { free_engine(e); delete e; return rc; }
+    *out = e;
+    return ORB_OK;
+}
+
+int orb_create(orb_engine** out, int64_t n, int device, int mode) {
+    return orb_create_sharded(out, n, 0, n, device, mode);
+}
+
+int orb_destroy(orb_engine* e) {
+    if (!e) return ORB_OK;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->stream);
+        free_engine(e);
+    }
+    delete e;
+    return ORB_OK;
+}
+
+int orb_set_params(orb_engine* e, double dt, double eps, double G) {
+    LOCK(e);
+    e->p.dt = dt;
+    e->p.h = 0.5 * dt;            // `0.5 * dt * acc` parses as (0.5*dt)*acc  (engine.py:70)
+    e->p.dt32 = (float)dt;        // NEP-50 weak scalar -> float32(dt)          (engine.py:74)
+    e->p.eps2 = eps * eps;        // physics.py:134
+    e->p.G = G;
+    drop_graphs(e);
+    return ORB_OK;
+}
+
+int orb_set_mode(orb_engine* e, int mode) {
+    LOCK(e);
+    if (mode != ORB_MODE_FAITHFUL && mode != ORB_MODE_FAST) return fail(ORB_ERR_INVALID, "bad mode");
+    e->mode = mode;
+    e->plan_valid = false;
+    drop_graphs(e);
+    return ORB_OK;
+}
+
+int orb_set_history(orb_engine* e, int64_t capacity) {
+    LOCK(e);
+    if (capacity < 0) return fail(ORB_ERR_INVALID, "negative capacity");
+    if (e->sharded && capacity > 0) return fail(ORB_ERR_INVALID, "history ring is not available on sharded engines");
+    CU(cudaStreamSynchronize(e->stream));
+    drop_graphs(e);
+    if (e->s.hist) { cudaFree(e->s.hist); e->s.hist = nullptr; }
+    e->s.hist_cap = 0;
+    if (capacity > 0) {
+        CU(cudaMalloc(&e->s.hist, sizeof(double) * 3 * e->s.n * capacity));
+        e->s.hist_cap = capacity;
+    }
+    ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 1);
+    CU(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orb_set_stream(orb_engine* e, void* cuda_stream) {
+    LOCK(e);
+    CU(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return ORB_OK;
+}
+
+int orb_upload(orb_engine* e, const double* x, const double* y, const double* z, const double* vx,
+               const double* vy, const double* vz, const double* m, const double* radius,
+               const uint8_t* vel_is_f32) {
+    LOCK(e);
+    if (!x || !y || !z || !vx || !vy || !vz || !m || !radius) return fail(ORB_ERR_INVALID, "null array");
+    const long long n = e->s.n;
+    const size_t nb = sizeof(double) * n;
+    cudaStream_t st = e->stream;
+    CU(cudaMemcpyAsync(e->d_stage, x, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->d_stage + n, y, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->d_stage + 2 * n, z, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->d_stage + 3 * n, m, nb, cudaMemcpyHostToDevice, st));
+    CU(launch_pack(e->s.pos4, e->d_stage, e->d_stage + n, e->d_stage + 2 * n, e->d_stage + 3 * n, n, st));
+    ++e->launches;
+    CU(cudaMemcpyAsync(e->s.vel, vx, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->s.vel + n, vy, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->s.vel + 2 * n, vz, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->s.radius, radius, nb, cudaMemcpyHostToDevice, st));
+    if (vel_is_f32)
+        CU(cudaMemcpyAsync(e->s.vf32, vel_is_f32, n, cudaMemcpyHostToDevice, st));
+    else
+        CU(cudaMemsetAsync(e->s.vf32, 0, n, st));
+    // overlap-prefilter bounds (largest two radii) for the fast kernel
+    double r1 = 0.0, r2 = 0.0;
+    long long i1 = -1;
+    for (long long i = 0; i < n; ++i) {
+        const double r = radius[i];
+        if (r > r1) { r2 = r1; r1 = r; i1 = i; }
+        else if (r > r2) { r2 = r; }
+    }
+    const bool detect = r1 > 0.0;      // all radii zero: a contact can only be dist == 0, a no-op (physics.py:396)
+    if (detect != e->detect || r1 != e->p.rmax1 || r2 != e->p.rmax2 || i1 != e->p.rmax1_idx) drop_graphs(e);
+    e->detect = detect;
+    e->p.detect = detect;
+    e->p.rmax1 = r1; e->p.rmax2 = r2; e->p.rmax1_idx = i1;
+    CU(cudaStreamSynchronize(st));     // host buffers may be reused by the caller
+    e->have_state = true;
+    return ORB_OK;
+}
+
+int orb_download_state(orb_engine* e, double* x, double* y, double* z, double* vx, double* vy, double* vz) {
+    LOCK(e);
+    const long long n = e->s.n;
+    const size_t nb = sizeof(double) * n;
+    cudaStream_t st = e->stream;
+    if (x || y || z) {
+        CU(launch_unpack(e->s.pos4, e->d_stage, e->d_stage + n, e->d_stage + 2 * n, n, st));
+        ++e->launches;
+        if (x) CU(cudaMemcpyAsync(x, e->d_stage, nb, cudaMemcpyDeviceToHost, st));
+        if (y) CU(cudaMemcpyAsync(y, e->d_stage + n, nb, cudaMemcpyDeviceToHost, st));
+        if (z) CU(cudaMemcpyAsync(z, e->d_stage + 2 * n, nb, cudaMemcpyDeviceToHost, st));
+    }
+    if (vx) CU(cudaMemcpyAsync(vx, e->s.vel, nb, cudaMemcpyDeviceToHost, st));
+    if (vy) CU(cudaMemcpyAsync(vy, e->s.vel + n, nb, cudaMemcpyDeviceToHost, st));
+    if (vz) CU(cudaMemcpyAsync(vz, e->s.vel + 2 * n, nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orb_download_acc(orb_engine* e, double* ax, double* ay, double* az) {
+    LOCK(e);
+    const long long n = e->s.n;
+    const size_t nb = sizeof(double) * n;
+    if (ax) CU(cudaMemcpyAsync(ax, e->s.acc, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (ay) CU(cudaMemcpyAsync(ay, e->s.acc + n, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (az) CU(cudaMemcpyAsync(az, e->s.acc + 2 * n, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return ORB_OK;
+}
+
+int orb_upload_acc(orb_engine* e, const double* ax, const double* ay, const double* az) {
+    LOCK(e);
+    if (!ax || !ay || !az) return fail(ORB_ERR_INVALID, "null array");
+    const long long n = e->s.n;
+    const size_t nb = sizeof(double) * n;
+    CU(cudaMemcpyAsync(e->s.acc, ax, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->s.acc + n, ay, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->s.acc + 2 * n, az, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return ORB_OK;
+}
+
+int orb_accel(orb_engine* e) {
+    LOCK(e);
+    if (!e->have_state) return fail(ORB_ERR_INVALID, "orb_accel before orb_upload");
+    ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 0);
+    CU(cudaGetLastError());
+    int launches = 1;
+    int rc = enqueue_force(e, false, &launches);
+    e->launches += launches;
+    return rc;
+}
+
+int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_overlaps) {
+    LOCK(e);
+    if (!e->have_state) return fail(ORB_ERR_INVALID, "orb_step before orb_upload");
+    if (nsteps < 0) return fail(ORB_ERR_INVALID, "negative nsteps");
+    if (e->sharded) return fail(ORB_ERR_INVALID, "sharded engines step with orb_step_begin/orb_step_finish");
+    cudaStream_t st = e->stream;
+    ctl_reset_kernel<<<1, 1, 0, st>>>(e->s.ctl, 0);
+    CU(cudaGetLastError());
+    ++e->launches;
+    if (nsteps > 0) {
+        if (use_tiny(e)) {
+            CU(launch_tiny_steps(e->s, e->p, nsteps, e->detect, st));
+            ++e->launches;
+        } else if (nsteps == 1) {
+            int launches = 0;
+            int rc = enqueue_step(e, &launches);
+            e->launches += launches;
+            if (rc) return rc;
+        } else {
+            int64_t left = nsteps;
+            if (left >= kGraphSteps) {
+                if (!e->graphK) { int rc = build_graph(e, kGraphSteps, &e->graphK); if (rc) return rc; }
+                while (left >= kGraphSteps) {
+                    CU(cudaGraphLaunch(e->graphK, st));
+                    e->launches += (long long)e->kernels_per_step * kGraphSteps;
+                    left -= kGraphSteps;
+                }
+            }
+            if (left > 0) {
+                if (!e->graph1) { int rc = build_graph(e, 1, &e->graph1); if (rc) return rc; }
+                for (; left > 0; --left) {
+                    CU(cudaGraphLaunch(e->graph1, st));
+                    e->launches += e->kernels_per_step;
+                }
+            }
+        }
+    }
+    CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (steps_done) *steps_done = e->h_ctl->steps_done;
+    if (n_overlaps) *n_overlaps = (int64_t)e->h_ctl->overlap_count;
+    return ORB_OK;
+}
+
+int orb_overlap_pairs(orb_engine* e, int64_t* pairs_ij, int64_t cap, int64_t* count) {
+    LOCK(e);
+    if (!count) return fail(ORB_ERR_INVALID, "null count");
+    CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const int64_t total = e->h_ctl->overlap_count;
+    *count = total;
+    const int64_t stored = std::min<int64_t>(std::min<int64_t>(total, kOverlapCap), cap);
+    if (pairs_ij && stored > 0) {
+        CU(cudaMemcpyAsync(pairs_ij, e->s.pairs, sizeof(long long) * 2 * stored, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    if (total > kOverlapCap) *count = total;   // caller sees count > cap -> full sweep
+    return ORB_OK;
+}
+
+int orb_step_begin(orb_engine* e) {
+    LOCK(e);
+    if (!e->have_state) return fail(ORB_ERR_INVALID, "step before upload");
+    CU(launch_kick_drift(e->s, e->p, e->stream));
+    ++e->launches;
+    return ORB_OK;
+}
+
+int orb_step_finish(orb_engine* e) {
+    LOCK(e);
+    int launches = 0;
+    int rc = enqueue_force(e, false, &launches);
+    if (rc) return rc;
+    CU(launch_kick_hist(e->s, e->p, e->stream));
+    e->launches += launches + 1;
+    return ORB_OK;
+}
+
+int orb_step_kick(orb_engine* e) {
+    LOCK(e);
+    CU(launch_kick_hist(e->s, e->p, e->stream));
+    CU(launch_advance(e->s, e->stream));
+    e->launches += 2;
+    return ORB_OK;
+}
+
+int orb_synchronize(orb_engine* e) {
+    LOCK(e);
+    CU(cudaStreamSynchronize(e->stream));
+    return ORB_OK;
+}
+
+int orb_pos4_ptr(orb_engine* e, void** device_ptr, int64_t* n_bodies) {
+    LOCK(e);
+    if (device_ptr) *device_ptr = e->s.pos4;
+    if (n_bodies) *n_bodies = e->s.n;
+    return ORB_OK;
+}
+
+int orb_vel_ptr(orb_engine* e, void** device_ptr) {
+    LOCK(e);
+    if (device_ptr) *device_ptr = e->s.vel;
+    return ORB_OK;
+}
+
+int orb_acc_ptr(orb_engine* e, void** device_ptr) {
+    LOCK(e);
+    if (device_ptr) *device_ptr = e->s.acc;
+    return ORB_OK;
+}
+
+int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, int* block, int* smem_bytes,
+                          int* launches_per_step) {
+    LOCK(e);
+    const char* nm;
+    int g = 0, b = 0, sm = 0, lps = 4;
+    if (use_tiny(e)) {
+        nm = "tiny_steps_kernel";
+        g = 1; b = std::max(32, (int)((e->s.n + 31) / 32) * 32);
+        sm = (int)(e->s.n * 40 + 16); lps = 1;
+    } else if (e->mode == ORB_MODE_FAST) {
+        int rc = ensure_plan(e);
+        if (rc) return rc;
+        nm = fast_kernel_name(e->plan.ti, e->detect);
+        g = e->plan.grid; b = e->plan.block; sm = e->plan.smem;
+        lps = 4 + (e->plan.slabs > 1 ? 1 : 0);
+    } else {
+        nm = "force_faithful_kernel";
+        faithful_geometry(e->s.tgt_hi - e->s.tgt_lo, &g, &b);
+        sm = b * 40;
+    }
+    if (name && name_len > 0) { strncpy(name, nm, name_len - 1); name[name_len - 1] = 0; }
+    if (grid) *grid = g;
+    if (block) *block = b;
+    if (smem_bytes) *smem_bytes = sm;
+    if (launches_per_step) *launches_per_step = lps;
+    return ORB_OK;
+}
+
+int orb_launch_count(orb_engine* e, int64_t* launches) {
+    LOCK(e);
+    if (launches) *launches = e->launches;
+    return ORB_OK;
+}
+
+int orb_potential(orb_engine* e, double* U) {
+    LOCK(e);
+    if (!U) return fail(ORB_ERR_INVALID, "null U");
+    const bool ordered = (e->mode == ORB_MODE_FAITHFUL) && e->s.n <= 4096;
+    int launches = 0;
+    CU(launch_potential(e->s, e->p, ordered, e->d_diag, e->stream, &launches));
+    e->launches += launches;
+    CU(cudaMemcpyAsync(e->h_diag, e->d_diag, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *U = e->h_diag[0];
+    return ORB_OK;
+}
+
+int orb_energy_angmom(orb_engine* e, double* K, double* L3) {
+    LOCK(e);
+    int launches = 0;
+    CU(launch_energy_angmom(e->s, e->d_diag, e->stream, &launches));
+    e->launches += launches;
+    CU(cudaMemcpyAsync(e->h_diag, e->d_diag, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (K) *K = e->h_diag[0];
+    if (L3) { L3[0] = e->h_diag[1]; L3[1] = e->h_diag[2]; L3[2] = e->h_diag[3]; }
+    return ORB_OK;
+}
+
+int orb_history_count(orb_engine* e, int64_t* total_appended) {
+    LOCK(e);
+    CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (total_appended) *total_appended = e->h_ctl->hist_count;
+    return ORB_OK;
+}
+
+int orb_history_append(orb_engine* e) {
+    LOCK(e);
+    if (e->s.hist_cap <= 0) return ORB_OK;
+    CU(launch_hist_append(e->s, e->stream));
+    e->launches += 2;
+    return ORB_OK;
+}
+
+int orb_history_download(orb_engine* e, int64_t last_k, double* out, int64_t* got) {
+    LOCK(e);
+    if (!got) return fail(ORB_ERR_INVALID, "null got");
+    *got = 0;
+    if (e->s.hist_cap <= 0 || last_k <= 0) return ORB_OK;
+    CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const long long total = e->h_ctl->hist_count;
+    const long long stored = std::min<long long>(total, e->s.hist_cap);
+    const long long k = std::min<long long>(last_k, stored);
+    if (k <= 0 || !out) { *got = k; return ORB_OK; }
+    const long long row = 3 * e->s.n;
+    const long long first = total - k;                  // logical index of the oldest wanted snapshot
+    long long done = 0;
+    while (done < k) {
+        const long long slot = (first + done) % e->s.hist_cap;
+        const long long run = std::min<long long>(k - done, e->s.hist_cap - slot);
+        CU(cudaMemcpyAsync(out + done * row, e->s.hist + slot * row, sizeof(double) * row * run,
+                           cudaMemcpyDeviceToHost, e->stream));
+        done += run;
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    *got = k;
+    return ORB_OK;
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// Ensemble
+// ===========================================================================
+struct orb_ensemble {
+    std::mutex mu;
+    int device = 0;
+    int mode = ORB_MODE_FAST;
+    EnsArgs a{};
+    double* base = nullptr;     // 10 planes of nsys*nb doubles
+    double* d_E = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    long long launches = 0;
+    bool have_state = false;
+};
+
+extern "C" {
+
+int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int mode, int vel_f32) {
+    if (!out) return fail(ORB_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (nsys <= 0 || nbody < 2 || nbody > 32) return fail(ORB_ERR_INVALID, "need nsys > 0 and 2 <= nbody <= 32");
+    if (mode != ORB_MODE_FAITHFUL && mode != ORB_MODE_FAST) return fail(ORB_ERR_INVALID, "bad mode");
+    int rc = select_device(device);
+    if (rc) return rc;
+    orb_ensemble* s = new orb_ensemble();
+    s->device = device;
+    s->mode = mode;
+    const long long tot = nsys * (long long)nbody;
+    cudaError_t ce = cudaMalloc(&s->base, sizeof(double) * 10 * tot);
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->d_E, sizeof(double) * nsys);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { cudaFree(s->base); cudaFree(s->d_E); delete s; return cuda_fail(ce, "ensemble alloc"); }
+    s->stream = s->own_stream;
+    double* b = s->base;
+    s->a.x = b; s->a.y = b + tot; s->a.z = b + 2 * tot; s->a.vx = b + 3 * tot; s->a.vy = b + 4 * tot;
+    s->a.vz = b + 5 * tot; s->a.ax = b + 6 * tot; s->a.ay = b + 7 * tot; s->a.az = b + 8 * tot; s->a.m = b + 9 * tot;
+    s->a.nsys = nsys;
+    s->a.nb = nbody;
+    int nbp = 1;
+    while (nbp < nbody) nbp <<= 1;
+    s->a.nbp = nbp;
+    s->a.vel_f32 = vel_f32 ? 1 : 0;
+    s->a.dt = 1.0; s->a.h = 0.5; s->a.dt32 = 1.0f; s->a.eps2 = 0.0; s->a.G = 6.67430e-11;
+    *out = s;
+    return ORB_OK;
+}
+
+int orb_ens_destroy(orb_ensemble* s) {
+    if (!s) return ORB_OK;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        cudaFree(s->base); cudaFree(s->d_E);
+        if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    }
+    delete s;
+    return ORB_OK;
+}
+
+int orb_ens_set_params(orb_ensemble* s, double dt, double eps, double G) {
+    LOCK(s);
+    s->a.dt = dt; s->a.h = 0.5 * dt; s->a.dt32 = (float)dt; s->a.eps2 = eps * eps; s->a.G = G;
+    return ORB_OK;
+}
+
+int orb_ens_set_stream(orb_ensemble* s, void* cuda_stream) {
+    LOCK(s);
+    CU(cudaStreamSynchronize(s->stream));
+    s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+    return ORB_OK;
+}
+
+int orb_ens_upload(orb_ensemble* s, const double* x, const double* y, const double* z, const double* vx,
+                   const double* vy, const double* vz, const double* m) {
+    LOCK(s);
+    if (!x || !y || !z || !vx || !vy || !vz || !m) return fail(ORB_ERR_INVALID, "null array");
+    const size_t nb = sizeof(double) * s->a.nsys * s->a.nb;
+    cudaStream_t st = s->stream;
+    CU(cudaMemcpyAsync(s->a.x, x, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->a.y, y, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->a.z, z, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->a.vx, vx, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->a.vy, vy, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->a.vz, vz, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(const_cast<double*>(s->a.m), m, nb, cudaMemcpyHostToDevice, st));
+    EnsArgs a = s->a;
+    a.nsteps = 0;
+    CU(launch_ens_accel(a, s->mode == ORB_MODE_FAITHFUL, st));     // engine.py:41
+    ++s->launches;
+    CU(cudaStreamSynchronize(st));
+    s->have_state = true;
+    return ORB_OK;
+}
+
+int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
+    LOCK(s);
+    if (!s->have_state) return fail(ORB_ERR_INVALID, "step before upload");
+    if (nsteps < 0) return fail(ORB_ERR_INVALID, "negative nsteps");
+    EnsArgs a = s->a;
+    const bool faithful = s->mode == ORB_MODE_FAITHFUL;
+    if (fused) {
+        a.nsteps = nsteps;
+        if (nsteps > 0) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
+    } else {
+        a.nsteps = 1;
+        for (int64_t k = 0; k < nsteps; ++k) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
+    }
+    return ORB_OK;
+}
+
+int orb_ens_download(orb_ensemble* s, double* x, double* y, double* z, double* vx, double* vy, double* vz) {
+    LOCK(s);
+    const size_t nb = sizeof(double) * s->a.nsys * s->a.nb;
+    cudaStream_t st = s->stream;
+    if (x) CU(cudaMemcpyAsync(x, s->a.x, nb, cudaMemcpyDeviceToHost, st));
+    if (y) CU(cudaMemcpyAsync(y, s->a.y, nb, cudaMemcpyDeviceToHost, st));
+    if (z) CU(cudaMemcpyAsync(z, s->a.z, nb, cudaMemcpyDeviceToHost, st));
+    if (vx) CU(cudaMemcpyAsync(vx, s->a.vx, nb, cudaMemcpyDeviceToHost, st));
+    if (vy) CU(cudaMemcpyAsync(vy, s->a.vy, nb, cudaMemcpyDeviceToHost, st));
+    if (vz) CU(cudaMemcpyAsync(vz, s->a.vz, nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orb_ens_energy(orb_ensemble* s, double* E_per_system) {
+    LOCK(s);
+    if (!E_per_system) return fail(ORB_ERR_INVALID, "null array");
+    CU(launch_ens_energy(s->a, s->d_E, s->stream));
+    ++s->launches;
+    CU(cudaMemcpyAsync(E_per_system, s->d_E, sizeof(double) * s->a.nsys, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return ORB_OK;
+}
+
+int orb_ens_synchronize(orb_ensemble* s) {
+    LOCK(s);
+    CU(cudaStreamSynchronize(s->stream));
+    return ORB_OK;
+}
+
+int orb_ens_launch_count(orb_ensemble* s, int64_t* launches) {
+    LOCK(s);
+    if (launches) *launches = s->launches;
+    return ORB_OK;
+}
+
+}  // extern "C"

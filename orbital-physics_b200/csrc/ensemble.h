@@ -1,0 +1,18 @@
+// ensemble.h -- launch interface of ensemble.cu
+#pragma once
+#include <cuda_runtime.h>
+namespace orb {
+struct EnsArgs {
+    double *x, *y, *z, *vx, *vy, *vz, *ax, *ay, *az;
+    const double* m;
+    long long nsys;
+    int nb, nbp;
+    long long nsteps;
+    double h, dt, eps2, G;
+    float dt32;
+    int vel_f32;
+};
+cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st);
+cudaError_t launch_ens_accel(const EnsArgs& a, bool faithful, cudaStream_t st);
+cudaError_t launch_ens_energy(const EnsArgs& a, double* E, cudaStream_t st);
+}  // namespace orb

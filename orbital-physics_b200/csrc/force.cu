@@ -1,0 +1,443 @@
+// force.cu -- all-pairs softened Newtonian acceleration kernels (sm_100a).
+//
+// Replaces pairwise_accelerations (reference core/physics.py:125-159) and the
+// overlap *detection* half of ObjectCollection.handle_collisions
+// (core/physics.py:513-518).
+//
+//   force_fast_kernel<TI,DETECT>   roofline kernel. Source bodies {x,y,z,m} are
+//       streamed through a 4-stage shared-memory ring by 1-D bulk TMA
+//       (cp.async.bulk + mbarrier, SASS UBLKCP); every thread keeps TI targets
+//       and their accumulators in registers and reads each source with two
+//       broadcast LDS.128. Per interaction: 3 DADD + 3 DFMA (r^2) + MUFU.RSQ64H
+//       seed + 7 DMUL/DFMA (m * r^-3 to full fp64 accuracy) + 3 DFMA = 16 FP64
+//       pipe instructions. FP64-pipe bound; HBM traffic is 56 B/body/pass.
+//       Work is a 2-D grid of (target block x source slab) items sized to fill
+//       148 SMs in whole waves; slab partials are combined in fixed order.
+//   force_faithful_kernel<DETECT>  bit-exact: one thread per target, ascending j,
+//       the reference's rounding sequence with IEEE sqrt/div.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "kernels.h"
+
+namespace orb {
+
+// ===========================================================================
+// Fast kernel
+// ===========================================================================
+constexpr int kFastThreads = 128;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kTile = 256;     // source bodies per TMA tile (8 KiB)
+constexpr int kStages = 4;
+
+struct FastArgs {
+    const double4* pos4;
+    const double* radius;
+    double* out;               // acc (3 x out_n SoA) when slabs == 1, else scratch (slabs x 3 x n_tgt)
+    long long out_n;           // SoA stride of `out`
+    long long out_off;         // index offset of target tgt_lo inside `out`
+    long long slab_stride;     // elements between slab partial planes (0 when slabs == 1)
+    long long n_src, tgt_lo, n_tgt;
+    int slabs, tiles_per_slab, n_tiles;
+    double eps2, G;
+    double rmax1, rmax2;
+    long long rmax1_idx;
+    Ctl* ctl;
+    long long* pairs;
+};
+
+// m_j * (r^2)^(-3/2) to ~1 ulp from the 20-bit MUFU seed:
+//   y0 = rsqrt(r2)(1+d), e = 1 - r2*y0^2,  (r2)^(-3/2) = y0^3 (1-e)^(-3/2)
+//   (1-e)^(-3/2) = 1 + 3/2 e + 15/8 e^2 + O(e^3),  |e| <~ 2^-19  => O(e^3) < 1e-17
+__device__ __forceinline__ double inv_r3_mass(double r2, double mj, int& y0_hi) {
+    const double y0 = rsqrt_seed(r2);
+    y0_hi = __double2hiint(y0);
+    const double u = y0 * y0;                 // exact: y0 has <= 21 significant bits
+    const double e = fma(-r2, u, 1.0);
+    const double c = mj * y0;
+    const double w = c * u;
+    const double p = fma(1.875, e, 1.5);
+    const double q = e * p;
+    return fma(w, q, w);
+}
+
+template <int TI, bool DETECT, bool CHECKED>
+__device__ __forceinline__ void tile_loop(const double2* __restrict__ tile, int cnt, long long j0, double eps2,
+                                          const double (&xi)[TI], const double (&yi)[TI], const double (&zi)[TI],
+                                          const long long (&idx)[TI], double (&ax)[TI], double (&ay)[TI],
+                                          double (&az)[TI], int (&maxhi)[TI]) {
+#pragma unroll 2
+    for (int j = 0; j < cnt; ++j) {
+        const double2 a = tile[2 * j];
+        const double2 b = tile[2 * j + 1];
+#pragma unroll
+        for (int k = 0; k < TI; ++k) {
+            const double dx = a.x - xi[k];
+            const double dy = a.y - yi[k];
+            const double dz = b.x - zi[k];
+            const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+            int hi;
+            double s = inv_r3_mass(r2, b.y, hi);
+            if (CHECKED) {
+                const bool self = (j0 + j) == idx[k];
+                s = self ? 0.0 : s;
+                hi = self ? 0 : hi;
+            }
+            if (DETECT) maxhi[k] = max(maxhi[k], hi);
+            ax[k] = fma(s, dx, ax[k]);
+            ay[k] = fma(s, dy, ay[k]);
+            az[k] = fma(s, dz, az[k]);
+        }
+    }
+}
+
+// Rare path: a seed exceeded the conservative threshold -- test the tile exactly.
+__device__ __noinline__ void rescan_tile(const double2* tile, int cnt, long long j0, long long i, double xi,
+                                         double yi, double zi, double Ri, const double* __restrict__ radius,
+                                         Ctl* ctl, long long* pairs) {
+    for (int j = 0; j < cnt; ++j) {
+        const long long jg = j0 + j;
+        if (jg <= i) continue;                      // each unordered pair once (i < j)
+        const double2 a = tile[2 * j];
+        const double2 b = tile[2 * j + 1];
+        // handle_collisions forms ri - rj (physics.py:517); squares are sign-independent
+        if (overlap_exact(xi - a.x, yi - a.y, zi - b.x, Ri, radius[jg])) record_overlap(ctl, pairs, i, jg);
+    }
+}
+
+template <int TI, bool DETECT>
+__global__ void __launch_bounds__(kFastThreads, (TI >= 6 ? 2 : (TI >= 3 ? 3 : 4)))
+force_fast_kernel(const FastArgs g) {
+    if (g.ctl->halted) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* tiles = reinterpret_cast<double2*>(smem_raw);                       // kStages x kTile x 2 double2
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTile * 32);
+    uint64_t* empty = full + kStages;
+
+    const int tid = threadIdx.x;
+    const int slab = blockIdx.x % g.slabs;
+    const long long tblock = blockIdx.x / g.slabs;
+    const long long cta_lo = g.tgt_lo + tblock * (long long)(kFastThreads * TI);
+    const long long tgt_hi = g.tgt_lo + g.n_tgt;
+    const long long cta_hi = min(cta_lo + (long long)(kFastThreads * TI), tgt_hi);
+
+    const int tile_lo = slab * g.tiles_per_slab;
+    const int tile_hi = min(tile_lo + g.tiles_per_slab, g.n_tiles);
+    const int ntiles = tile_hi - tile_lo;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kFastWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {   // tile index relative to tile_lo
+        const int s = t % kStages;
+        const long long j0 = (long long)(tile_lo + t) * kTile;
+        const int cnt = (int)min((long long)kTile, g.n_src - j0);
+        const uint32_t bytes = (uint32_t)cnt * 32u;
+        mbar_expect_tx(&full[s], bytes);
+        tma_load_1d(tiles + (size_t)s * kTile * 2, g.pos4 + j0, bytes, &full[s]);
+    };
+    if (tid == 0) {
+        const int pre = min(kStages, ntiles);
+        for (int t = 0; t < pre; ++t) issue(t);
+    }
+
+    double xi[TI], yi[TI], zi[TI], ax[TI], ay[TI], az[TI];
+    long long idx[TI];
+    int maxhi[TI], thr[TI];
+    double Ri[TI];
+#pragma unroll
+    for (int k = 0; k < TI; ++k) {
+        idx[k] = cta_lo + (long long)k * kFastThreads + tid;
+        const long long ld = min(idx[k], tgt_hi - 1);      // tail threads shadow the last target, never store
+        const double4 p = g.pos4[ld];
+        xi[k] = p.x; yi[k] = p.y; zi[k] = p.z;
+        ax[k] = ay[k] = az[k] = 0.0;
+        maxhi[k] = 0;
+        thr[k] = 0x7fffffff;
+        Ri[k] = 0.0;
+        if (DETECT) {
+            Ri[k] = g.radius[ld];
+            const double partner = (ld == g.rmax1_idx) ? g.rmax2 : g.rmax1;
+            const double rs = Ri[k] + partner;
+            // overlap => r2 <= rs^2(1+tiny) + eps2 => seed >= rsqrt(rs^2+eps2) (1 - 2^-19)
+            const double bound = (1.0 / sqrt(fma(rs, rs, g.eps2))) * (1.0 - 1.52587890625e-05);
+            thr[k] = __double2hiint(bound) - 1;
+        }
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kStages;
+        mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
+        const double2* tile = tiles + (size_t)s * kTile * 2;
+        const long long j0 = (long long)(tile_lo + t) * kTile;
+        const int cnt = (int)min((long long)kTile, g.n_src - j0);
+        const bool diag = (j0 < cta_hi) && (j0 + cnt > cta_lo);        // CTA-uniform
+        if (diag)
+            tile_loop<TI, DETECT, true>(tile, cnt, j0, g.eps2, xi, yi, zi, idx, ax, ay, az, maxhi);
+        else
+            tile_loop<TI, DETECT, false>(tile, cnt, j0, g.eps2, xi, yi, zi, idx, ax, ay, az, maxhi);
+        if (DETECT) {
+#pragma unroll
+            for (int k = 0; k < TI; ++k) {
+                if (maxhi[k] >= thr[k] && idx[k] < tgt_hi)
+                    rescan_tile(tile, cnt, j0, idx[k], xi[k], yi[k], zi[k], Ri[k], g.radius, g.ctl, g.pairs);
+                maxhi[k] = 0;
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        // refill the stage freed one tile ago: the producer never waits on the current tile's stragglers
+        if (tid == 0 && t >= 1 && (t - 1 + kStages) < ntiles) {
+            const int tp = t - 1;
+            mbar_wait(&empty[tp % kStages], (uint32_t)((tp / kStages) & 1));
+            issue(tp + kStages);
+        }
+    }
+
+    // epilogue
+    const double scale = (g.slabs == 1) ? g.G : 1.0;
+    double* ox = g.out + (long long)slab * g.slab_stride;
+#pragma unroll
+    for (int k = 0; k < TI; ++k) {
+        if (idx[k] < tgt_hi) {
+            const long long o = g.out_off + (idx[k] - g.tgt_lo);
+            ox[o] = scale * ax[k];
+            ox[o + g.out_n] = scale * ay[k];
+            ox[o + 2 * g.out_n] = scale * az[k];
+        }
+    }
+}
+
+// acc[i] = G * (((p_0 + p_1) + p_2) + ...)  -- fixed slab order: deterministic
+__global__ void __launch_bounds__(256) reduce_slabs_kernel(const double* __restrict__ scratch, double* acc,
+                                                           long long n_tgt, long long acc_n, long long acc_off,
+                                                           int slabs, double G, const Ctl* ctl) {
+    if (ctl->halted) return;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_tgt) return;
+    const long long plane = 3 * n_tgt;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double s = scratch[c * n_tgt + i];
+        for (int k = 1; k < slabs; ++k) s += scratch[k * plane + c * n_tgt + i];
+        acc[acc_off + i + c * acc_n] = G * s;
+    }
+}
+
+template <int TI, bool DETECT>
+static cudaError_t launch_fast_t(const FastArgs& a, const FastPlan& plan, cudaStream_t st) {
+    auto kern = force_fast_kernel<TI, DETECT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<plan.grid, plan.block, plan.smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int TI, bool DETECT>
+static int occupancy_t(int smem) {
+    int nb = 0;
+    auto kern = force_fast_kernel<TI, DETECT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kFastThreads, smem) != cudaSuccess) nb = 0;
+    return nb;
+}
+
+static int fast_smem_bytes() { return kStages * kTile * 32 + 2 * kStages * 8 + 64; }
+
+static int occupancy_for(int ti) {
+    const int smem = fast_smem_bytes();
+    switch (ti) {
+        case 1: return occupancy_t<1, false>(smem);
+        case 2: return occupancy_t<2, false>(smem);
+        case 4: return occupancy_t<4, false>(smem);
+        case 6: return occupancy_t<6, false>(smem);
+        default: return occupancy_t<8, false>(smem);
+    }
+}
+
+const char* fast_kernel_name(int ti, bool detect) {
+    static char buf[64];
+    snprintf(buf, sizeof buf, "force_fast_kernel<%d,%s>", ti, detect ? "true" : "false");
+    return buf;
+}
+
+// Choose targets-per-thread and the number of source slabs so that the grid is
+// (close to) a whole number of full waves of the 148 x ctas_per_sm resident slots.
+FastPlan plan_fast(long long n_tgt, long long n_src, int sm_count) {
+    FastPlan p;
+    const char* env_ti = getenv("ORBITAL_B200_TI");
+    const long long per_sm = (n_tgt + sm_count - 1) / sm_count;
+    int ti = per_sm >= 4 * 128 * 4 ? 4 : (per_sm >= 2 * 128 * 2 ? 2 : 1);
+    if (env_ti) {
+        const int v = atoi(env_ti);
+        if (v == 1 || v == 2 || v == 4 || v == 6 || v == 8) ti = v;
+    }
+    p.ti = ti;
+    p.block = kFastThreads;
+    p.smem = fast_smem_bytes();
+    int occ = occupancy_for(ti);
+    if (occ <= 0) occ = 2;
+    p.ctas_per_sm = occ;
+    const long long slots = (long long)sm_count * occ;
+    const long long tblocks = (n_tgt + (long long)kFastThreads * ti - 1) / ((long long)kFastThreads * ti);
+    const int n_tiles = (int)((n_src + kTile - 1) / kTile);
+    // candidate slab counts: best wave efficiency with at least ~6 waves when the problem is big enough
+    int best_s = 1;
+    double best_eff = -1.0;
+    const int max_s = (int)std::min<long long>(n_tiles, 64);
+    const char* env_s = getenv("ORBITAL_B200_SLABS");
+    for (int s = 1; s <= max_s; ++s) {
+        const int tps = (n_tiles + s - 1) / s;
+        const int s_eff = (n_tiles + tps - 1) / tps;      // slabs actually non-empty
+        if (s_eff != s) continue;
+        const long long items = tblocks * s;
+        const long long waves = (items + slots - 1) / slots;
+        // every item costs tps tiles (last slab may be shorter: ignore); time ~ waves * tps
+        const double eff = (double)n_tiles * tblocks / ((double)waves * slots * tps);
+        // mild penalty per extra slab (partial-sum traffic + reduce launch)
+        const double score = eff - 0.002 * (s - 1) - (s > 1 ? 0.01 : 0.0);
+        if (score > best_eff) { best_eff = score; best_s = s; }
+    }
+    if (env_s) {
+        const int v = atoi(env_s);
+        if (v >= 1 && v <= n_tiles) best_s = v;
+    }
+    p.tiles_per_slab = (n_tiles + best_s - 1) / best_s;
+    p.slabs = (n_tiles + p.tiles_per_slab - 1) / p.tiles_per_slab;
+    p.grid = (int)(tblocks * p.slabs);
+    return p;
+}
+
+cudaError_t launch_force_fast(const DeviceState& s, const StepParams& p, const FastPlan& plan, bool detect,
+                              cudaStream_t st, int* launches) {
+    FastArgs a;
+    const long long n_tgt = s.tgt_hi - s.tgt_lo;
+    a.pos4 = s.pos4;
+    a.radius = s.radius;
+    a.n_src = s.n;
+    a.tgt_lo = s.tgt_lo;
+    a.n_tgt = n_tgt;
+    a.slabs = plan.slabs;
+    a.tiles_per_slab = plan.tiles_per_slab;
+    a.n_tiles = (int)((s.n + kTile - 1) / kTile);
+    a.eps2 = p.eps2;
+    a.G = p.G;
+    a.rmax1 = p.rmax1;
+    a.rmax2 = p.rmax2;
+    a.rmax1_idx = p.rmax1_idx;
+    a.ctl = s.ctl;
+    a.pairs = s.pairs;
+    if (plan.slabs == 1) {
+        a.out = s.acc; a.out_n = s.n; a.out_off = s.tgt_lo; a.slab_stride = 0;
+    } else {
+        a.out = s.scratch; a.out_n = n_tgt; a.out_off = 0; a.slab_stride = 3 * n_tgt;
+    }
+    cudaError_t e;
+#define ORB_FAST_CASE(T)                                                                        \
+    case T:                                                                                     \
+        e = detect ? launch_fast_t<T, true>(a, plan, st) : launch_fast_t<T, false>(a, plan, st); \
+        break;
+    switch (plan.ti) {
+        ORB_FAST_CASE(1)
+        ORB_FAST_CASE(2)
+        ORB_FAST_CASE(4)
+        ORB_FAST_CASE(6)
+        ORB_FAST_CASE(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef ORB_FAST_CASE
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    if (plan.slabs > 1) {
+        const int blk = 256;
+        const int grd = (int)((n_tgt + blk - 1) / blk);
+        reduce_slabs_kernel<<<grd, blk, 0, st>>>(s.scratch, s.acc, n_tgt, s.n, s.tgt_lo, plan.slabs, p.G, s.ctl);
+        e = cudaGetLastError();
+        if (launches) ++*launches;
+    }
+    return e;
+}
+
+// ===========================================================================
+// Faithful kernel: one thread per target, ascending j, exact rounding sequence
+// ===========================================================================
+template <bool DETECT>
+__global__ void force_faithful_kernel(const double4* __restrict__ pos4, const double* __restrict__ radius,
+                                      double* acc, long long n, long long tgt_lo, long long tgt_hi, double eps2,
+                                      double G, Ctl* ctl, long long* pairs) {
+    if (ctl->halted) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double4* sp = reinterpret_cast<double4*>(smem_raw);          // blockDim sources {x,y,z,G*m}
+    double* sr = reinterpret_cast<double*>(sp + blockDim.x);     // radii
+    const long long i = tgt_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool active = i < tgt_hi;
+    const long long li = active ? i : tgt_hi - 1;
+    const double4 me = pos4[li];
+    const double Ri = DETECT ? radius[li] : 0.0;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (long long j0 = 0; j0 < n; j0 += blockDim.x) {
+        const long long jl = j0 + threadIdx.x;
+        if (jl < n) {
+            double4 q = pos4[jl];
+            q.w = __dmul_rn(G, q.w);                             // G * mj  (physics.py:151)
+            sp[threadIdx.x] = q;
+            if (DETECT) sr[threadIdx.x] = radius[jl];
+        }
+        __syncthreads();
+        const int cnt = (int)min((long long)blockDim.x, n - j0);
+        if (active) {
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const long long jg = j0 + j;
+                if (jg == i) continue;
+                const double4 q = sp[j];
+                const double dx = __dsub_rn(q.x, me.x), dy = __dsub_rn(q.y, me.y), dz = __dsub_rn(q.z, me.z);
+                pair_faithful(dx, dy, dz, eps2, q.w, ax, ay, az);
+                if (DETECT && jg > i) {
+                    if (overlap_exact(-dx, -dy, -dz, Ri, sr[j])) record_overlap(ctl, pairs, i, jg);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (active) {
+        acc[i] = ax;
+        acc[i + n] = ay;
+        acc[i + 2 * n] = az;
+    }
+}
+
+void faithful_geometry(long long n_tgt, int* grid, int* block) {
+    const int b = n_tgt <= 32768 ? 32 : 128;
+    *block = b;
+    *grid = (int)((n_tgt + b - 1) / b);
+}
+
+cudaError_t launch_force_faithful(const DeviceState& s, const StepParams& p, bool detect, cudaStream_t st,
+                                  int* launches) {
+    int grid, block;
+    faithful_geometry(s.tgt_hi - s.tgt_lo, &grid, &block);
+    const size_t smem = (size_t)block * (sizeof(double4) + sizeof(double));
+    if (detect)
+        force_faithful_kernel<true><<<grid, block, smem, st>>>(s.pos4, s.radius, s.acc, s.n, s.tgt_lo, s.tgt_hi,
+                                                                p.eps2, p.G, s.ctl, s.pairs);
+    else
+        force_faithful_kernel<false><<<grid, block, smem, st>>>(s.pos4, s.radius, s.acc, s.n, s.tgt_lo, s.tgt_hi,
+                                                                 p.eps2, p.G, s.ctl, s.pairs);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace orb

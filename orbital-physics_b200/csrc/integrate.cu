@@ -1,0 +1,376 @@
+// integrate.cu -- leapfrog update kernels, the fused single-CTA multi-step kernel,
+// history ring writer and diagnostics reductions (sm_100a).
+//
+// Replaces SimulationEngine.step phases 1,2,4,6 (reference core/engine.py:69-75,
+// 81-82,88-92) and total_energy / angular_momentum (core/engine.py:104-121).
+// The arithmetic is the reference's exact rounding sequence in
+// both engine modes: these passes are O(N) and HBM-trivial next to the force pass.
+#include <algorithm>
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace orb {
+
+// ---------------------------------------------------------------------------
+// engine.py:69-75  half-kick + drift of the local targets; writes the packed
+// source array the force pass (and the multi-GPU all-gather) reads.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kick_drift_kernel(double4* pos4, double* vel, const double* __restrict__ acc,
+                                                         const uint8_t* __restrict__ vf32, long long n,
+                                                         long long lo, long long hi, double h, double dt,
+                                                         float dt32, const Ctl* ctl) {
+    if (ctl->halted) return;
+    const long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const bool f32 = vf32[i] != 0;
+    const double vx = kick_faithful(vel[i], h, acc[i], f32);
+    const double vy = kick_faithful(vel[i + n], h, acc[i + n], f32);
+    const double vz = kick_faithful(vel[i + 2 * n], h, acc[i + 2 * n], f32);
+    vel[i] = vx; vel[i + n] = vy; vel[i + 2 * n] = vz;
+    double4 p = pos4[i];
+    p.x = drift_faithful(p.x, vx, dt, dt32, f32);
+    p.y = drift_faithful(p.y, vy, dt, dt32, f32);
+    p.z = drift_faithful(p.z, vz, dt, dt32, f32);
+    pos4[i] = p;
+}
+
+// engine.py:81-82 second half-kick, then engine.py:88-92 history append (skipped
+// in a halting step: the host appends after resolving the contacts).
+__global__ void __launch_bounds__(256) kick_hist_kernel(const double4* __restrict__ pos4, double* vel,
+                                                        const double* __restrict__ acc,
+                                                        const uint8_t* __restrict__ vf32, long long n, long long lo,
+                                                        long long hi, double h, double* hist, long long hist_cap,
+                                                        const Ctl* ctl) {
+    if (ctl->halted) return;
+    const long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const bool f32 = vf32[i] != 0;
+    vel[i] = kick_faithful(vel[i], h, acc[i], f32);
+    vel[i + n] = kick_faithful(vel[i + n], h, acc[i + n], f32);
+    vel[i + 2 * n] = kick_faithful(vel[i + 2 * n], h, acc[i + 2 * n], f32);
+    if (hist_cap > 0 && ctl->overlap_count == 0) {
+        const double4 p = pos4[i];
+        double* row = hist + ((ctl->hist_count % hist_cap) * n + i) * 3;
+        row[0] = p.x; row[1] = p.y; row[2] = p.z;
+    }
+}
+
+__global__ void advance_kernel(Ctl* ctl, long long hist_cap) {
+    if (ctl->halted) return;
+    ctl->steps_done += 1;
+    if (ctl->overlap_count > 0)
+        ctl->halted = 1;
+    else if (hist_cap > 0)
+        ctl->hist_count += 1;
+}
+
+__global__ void __launch_bounds__(256) hist_append_kernel(const double4* __restrict__ pos4, long long n,
+                                                          double* hist, long long hist_cap, const Ctl* ctl) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || hist_cap <= 0) return;
+    const double4 p = pos4[i];
+    double* row = hist + ((ctl->hist_count % hist_cap) * n + i) * 3;
+    row[0] = p.x; row[1] = p.y; row[2] = p.z;
+}
+
+__global__ void hist_bump_kernel(Ctl* ctl) { ctl->hist_count += 1; }
+
+static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+cudaError_t launch_kick_drift(const DeviceState& s, const StepParams& p, cudaStream_t st) {
+    const long long nt = s.tgt_hi - s.tgt_lo;
+    kick_drift_kernel<<<grid_for(nt, 256), 256, 0, st>>>(s.pos4, s.vel, s.acc, s.vf32, s.n, s.tgt_lo, s.tgt_hi, p.h,
+                                                         p.dt, p.dt32, s.ctl);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kick_hist(const DeviceState& s, const StepParams& p, cudaStream_t st) {
+    const long long nt = s.tgt_hi - s.tgt_lo;
+    kick_hist_kernel<<<grid_for(nt, 256), 256, 0, st>>>(s.pos4, s.vel, s.acc, s.vf32, s.n, s.tgt_lo, s.tgt_hi, p.h,
+                                                        s.hist, s.hist_cap, s.ctl);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advance(const DeviceState& s, cudaStream_t st) {
+    advance_kernel<<<1, 1, 0, st>>>(s.ctl, s.hist_cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hist_append(const DeviceState& s, cudaStream_t st) {
+    if (s.hist_cap <= 0) return cudaSuccess;
+    hist_append_kernel<<<grid_for(s.n, 256), 256, 0, st>>>(s.pos4, s.n, s.hist, s.hist_cap, s.ctl);
+    hist_bump_kernel<<<1, 1, 0, st>>>(s.ctl);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Fused small-system kernel: ONE CTA integrates the whole system for nsteps
+// steps (engine.py:65-97 per step) with all state in registers / shared memory.
+// Thread i owns body i; sources are broadcast from shared memory in ascending j
+// (bit-exact accumulation order). Two block barriers per step.
+// ---------------------------------------------------------------------------
+template <bool DETECT>
+__global__ void __launch_bounds__(kTinyMax) tiny_steps_kernel(double4* pos4, double* vel, double* acc,
+                                                              const double* __restrict__ radius,
+                                                              const uint8_t* __restrict__ vf32, int n,
+                                                              long long nsteps, double h, double dt, float dt32,
+                                                              double eps2, double G, double* hist,
+                                                              long long hist_cap, Ctl* ctl, long long* pairs) {
+    if (ctl->halted) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double4* sp = reinterpret_cast<double4*>(smem_raw);     // {x,y,z,G*m}
+    double* sr = reinterpret_cast<double*>(sp + n);
+    const int i = threadIdx.x;
+    const bool active = i < n;
+    double x = 0, y = 0, z = 0, gm = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, Ri = 0;
+    bool f32 = false;
+    if (active) {
+        const double4 p = pos4[i];
+        x = p.x; y = p.y; z = p.z;
+        gm = __dmul_rn(G, p.w);
+        vx = vel[i]; vy = vel[i + n]; vz = vel[i + 2 * n];
+        ax = acc[i]; ay = acc[i + n]; az = acc[i + 2 * n];
+        f32 = vf32[i] != 0;
+        Ri = radius[i];
+        sr[i] = Ri;
+    }
+    const long long hist0 = ctl->hist_count;
+    long long done = 0;
+    for (long long s = 0; s < nsteps; ++s) {
+        if (active) {
+            vx = kick_faithful(vx, h, ax, f32);                      // engine.py:69-70
+            vy = kick_faithful(vy, h, ay, f32);
+            vz = kick_faithful(vz, h, az, f32);
+            x = drift_faithful(x, vx, dt, dt32, f32);                // engine.py:73-75
+            y = drift_faithful(y, vy, dt, dt32, f32);
+            z = drift_faithful(z, vz, dt, dt32, f32);
+            sp[i] = make_double4(x, y, z, gm);
+        }
+        __syncthreads();
+        int hit = 0;
+        if (active) {
+            double bx = 0.0, by = 0.0, bz = 0.0;                     // physics.py:132
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const double4 q = sp[j];
+                const double dx = __dsub_rn(q.x, x), dy = __dsub_rn(q.y, y), dz = __dsub_rn(q.z, z);
+                pair_faithful(dx, dy, dz, eps2, q.w, bx, by, bz);
+                if (DETECT && j > i) {
+                    if (overlap_exact(-dx, -dy, -dz, Ri, sr[j])) {
+                        record_overlap(ctl, pairs, i, j);
+                        hit = 1;
+                    }
+                }
+            }
+            ax = bx; ay = by; az = bz;
+            vx = kick_faithful(vx, h, ax, f32);                      // engine.py:81-82
+            vy = kick_faithful(vy, h, ay, f32);
+            vz = kick_faithful(vz, h, az, f32);
+        }
+        const int hits = DETECT ? __syncthreads_or(hit) : (__syncthreads(), 0);
+        ++done;
+        if (hits) break;
+        if (active && hist_cap > 0) {                                // engine.py:88-92
+            double* row = hist + (((hist0 + s) % hist_cap) * n + i) * 3;
+            row[0] = x; row[1] = y; row[2] = z;
+        }
+    }
+    if (active) {
+        pos4[i] = make_double4(x, y, z, pos4[i].w);
+        vel[i] = vx; vel[i + n] = vy; vel[i + 2 * n] = vz;
+        acc[i] = ax; acc[i + n] = ay; acc[i + 2 * n] = az;
+    }
+    if (i == 0) {
+        ctl->steps_done += done;
+        if (ctl->overlap_count > 0) {
+            ctl->halted = 1;
+            if (hist_cap > 0) ctl->hist_count = hist0 + (done - 1);
+        } else if (hist_cap > 0) {
+            ctl->hist_count = hist0 + done;
+        }
+    }
+}
+
+cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long long nsteps, bool detect,
+                              cudaStream_t st) {
+    const int n = (int)s.n;
+    const int block = std::max(32, ((n + 31) / 32) * 32);
+    const size_t smem = (size_t)n * (sizeof(double4) + sizeof(double)) + 16;
+    if (detect)
+        tiny_steps_kernel<true><<<1, block, smem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h, p.dt,
+                                                        p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl, s.pairs);
+    else
+        tiny_steps_kernel<false><<<1, block, smem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h, p.dt,
+                                                         p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl, s.pairs);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// SoA <-> packed {x,y,z,m}
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_kernel(double4* pos4, const double* __restrict__ x,
+                                                   const double* __restrict__ y, const double* __restrict__ z,
+                                                   const double* __restrict__ m, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) pos4[i] = make_double4(x[i], y[i], z[i], m[i]);
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const double4* __restrict__ pos4, double* x, double* y,
+                                                     double* z, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double4 p = pos4[i];
+        x[i] = p.x; y[i] = p.y; z[i] = p.z;
+    }
+}
+
+cudaError_t launch_pack(double4* pos4, const double* x, const double* y, const double* z, const double* m,
+                        long long n, cudaStream_t st) {
+    pack_kernel<<<grid_for(n, 256), 256, 0, st>>>(pos4, x, y, z, m, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(const double4* pos4, double* x, double* y, double* z, long long n, cudaStream_t st) {
+    unpack_kernel<<<grid_for(n, 256), 256, 0, st>>>(pos4, x, y, z, n);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Potential energy  U = sum_{i<j} ((-G m_i) m_j) / sqrt(r2)   (physics.py:158)
+// ---------------------------------------------------------------------------
+// Reference order: one running sum over pairs in lexicographic (i, j>i) order.
+// The terms of a row chunk are produced by the whole CTA, then added by thread 0
+// in order, so the result is bit-identical to the Python loop.
+__global__ void __launch_bounds__(256) potential_faithful_kernel(const double4* __restrict__ pos4, int n,
+                                                                 double eps2, double G, double* out) {
+    __shared__ double terms[256];
+    double U = 0.0;
+    for (int i = 0; i < n - 1; ++i) {
+        const double4 pi = pos4[i];
+        const double gmi = __dmul_rn(-G, pi.w);                       // (-G * mi)
+        for (int j0 = i + 1; j0 < n; j0 += 256) {
+            const int j = j0 + threadIdx.x;
+            if (j < n) {
+                const double4 pj = pos4[j];
+                const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y), dz = __dsub_rn(pj.z, pi.z);
+                const double r2 = __dadd_rn(dot3_numpy(dx, dy, dz), eps2);
+                const double inv_r = __ddiv_rn(1.0, __dsqrt_rn(r2));
+                terms[threadIdx.x] = __dmul_rn(__dmul_rn(gmi, pj.w), inv_r);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int cnt = min(256, n - j0);
+                for (int k = 0; k < cnt; ++k) U = __dadd_rn(U, terms[k]);
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) *out = U;
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r;   // valid in warp 0
+}
+
+// Tree-order potential for large n: thread i sums its row (j > i), block + grid reduction.
+__global__ void __launch_bounds__(256) potential_tree_kernel(const double4* __restrict__ pos4, long long n,
+                                                             double eps2, double* partial) {
+    __shared__ double4 tile[256];
+    __shared__ double sh[8];
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long li = min(i, n - 1);
+    const double4 me = pos4[li];
+    double u = 0.0;
+    const long long jstart = (blockIdx.x * (long long)blockDim.x / 256) * 256;
+    for (long long j0 = jstart; j0 < n; j0 += 256) {
+        const long long jl = j0 + threadIdx.x;
+        if (jl < n) tile[threadIdx.x] = pos4[jl];
+        __syncthreads();
+        const int cnt = (int)min(256LL, n - j0);
+        for (int j = 0; j < cnt; ++j) {
+            if (j0 + j > i && i < n) {
+                const double4 q = tile[j];
+                const double dx = q.x - me.x, dy = q.y - me.y, dz = q.z - me.z;
+                const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+                u += q.w * (1.0 / sqrt(r2));
+            }
+        }
+        __syncthreads();
+    }
+    u *= me.w;
+    const double tot = block_sum_256(u, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) final_sum_kernel(const double* __restrict__ partial, int count, int ncomp,
+                                                        double scale0, double* out) {
+    __shared__ double sh[8];
+    for (int c = 0; c < ncomp; ++c) {
+        double v = 0.0;
+        for (int k = threadIdx.x; k < count; k += blockDim.x) v += partial[(long long)c * count + k];
+        const double tot = block_sum_256(v, sh);
+        if (threadIdx.x == 0) out[c] = (c == 0 ? scale0 : 1.0) * tot;
+    }
+}
+
+cudaError_t launch_potential(const DeviceState& s, const StepParams& p, bool faithful_order, double* d_out,
+                             cudaStream_t st, int* launches) {
+    if (faithful_order) {
+        potential_faithful_kernel<<<1, 256, 0, st>>>(s.pos4, (int)s.n, p.eps2, p.G, d_out);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+    const int grid = grid_for(s.n, 256);
+    potential_tree_kernel<<<grid, 256, 0, st>>>(s.pos4, s.n, p.eps2, s.reduce_buf);
+    final_sum_kernel<<<1, 256, 0, st>>>(s.reduce_buf, grid, 1, -p.G, d_out);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+// K = sum 1/2 m v.v ; L = sum r x (m v)     (engine.py:104-121, fp64)
+__global__ void __launch_bounds__(256) energy_angmom_kernel(const double4* __restrict__ pos4,
+                                                            const double* __restrict__ vel, long long n,
+                                                            long long lo, long long hi, double* partial,
+                                                            int nblocks) {
+    __shared__ double sh[8];
+    const long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double k = 0, lx = 0, ly = 0, lz = 0;
+    if (i < hi) {
+        const double4 p = pos4[i];
+        const double vx = vel[i], vy = vel[i + n], vz = vel[i + 2 * n];
+        k = 0.5 * p.w * (vx * vx + vy * vy + vz * vz);
+        const double px = p.w * vx, py = p.w * vy, pz = p.w * vz;
+        lx = p.y * pz - p.z * py;
+        ly = p.z * px - p.x * pz;
+        lz = p.x * py - p.y * px;
+    }
+    double t;
+    t = block_sum_256(k, sh);  if (threadIdx.x == 0) partial[0 * nblocks + blockIdx.x] = t;
+    t = block_sum_256(lx, sh); if (threadIdx.x == 0) partial[1 * nblocks + blockIdx.x] = t;
+    t = block_sum_256(ly, sh); if (threadIdx.x == 0) partial[2 * nblocks + blockIdx.x] = t;
+    t = block_sum_256(lz, sh); if (threadIdx.x == 0) partial[3 * nblocks + blockIdx.x] = t;
+}
+
+cudaError_t launch_energy_angmom(const DeviceState& s, double* d_out4, cudaStream_t st, int* launches) {
+    const long long nt = s.tgt_hi - s.tgt_lo;
+    const int grid = grid_for(nt, 256);
+    energy_angmom_kernel<<<grid, 256, 0, st>>>(s.pos4, s.vel, s.n, s.tgt_lo, s.tgt_hi, s.reduce_buf, grid);
+    final_sum_kernel<<<1, 256, 0, st>>>(s.reduce_buf, grid, 4, 1.0, d_out4);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace orb

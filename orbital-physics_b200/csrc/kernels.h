@@ -1,0 +1,76 @@
+// kernels.h -- host-visible launch interface between the translation units of liborbital_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace orb {
+
+// Resident state of one engine handle (device pointers).
+struct DeviceState {
+    long long n = 0;          // all bodies (sources)
+    long long tgt_lo = 0;     // locally integrated targets [tgt_lo, tgt_hi)
+    long long tgt_hi = 0;
+    double4* pos4 = nullptr;  // n x {x,y,z,m}
+    double* vel = nullptr;    // 3 x n (SoA: vx | vy | vz)
+    double* acc = nullptr;    // 3 x n
+    double* radius = nullptr; // n
+    uint8_t* vf32 = nullptr;  // n : velocity stored as float32 in the reference
+    Ctl* ctl = nullptr;
+    long long* pairs = nullptr;     // 2 x kOverlapCap
+    double* hist = nullptr;         // hist_cap x n x 3
+    long long hist_cap = 0;
+    double* scratch = nullptr;      // fast kernel partial sums: slabs x 3 x n_tgt
+    long long scratch_elems = 0;
+    double* reduce_buf = nullptr;   // diagnostics partials
+};
+
+struct StepParams {
+    double dt, h, eps2, G;
+    float dt32;
+    double rmax1, rmax2;      // largest / second-largest radius (fast-mode overlap prefilter)
+    long long rmax1_idx;
+    int detect;               // any radius > 0 (or coincident check wanted)
+};
+
+// Geometry chosen for the fast force kernel.
+struct FastPlan {
+    int ti = 1;               // targets per thread
+    int slabs = 1;            // source slabs (2-D decomposition)
+    int tiles_per_slab = 0;
+    int grid = 0;
+    int block = 128;
+    int smem = 0;
+    int ctas_per_sm = 0;
+};
+
+// ---- force.cu ----
+FastPlan plan_fast(long long n_tgt, long long n_src, int sm_count);
+cudaError_t launch_force_fast(const DeviceState& s, const StepParams& p, const FastPlan& plan, bool detect,
+                              cudaStream_t st, int* launches);
+cudaError_t launch_force_faithful(const DeviceState& s, const StepParams& p, bool detect, cudaStream_t st,
+                                  int* launches);
+void faithful_geometry(long long n_tgt, int* grid, int* block);
+const char* fast_kernel_name(int ti, bool detect);
+
+// ---- integrate.cu ----
+cudaError_t launch_kick_drift(const DeviceState& s, const StepParams& p, cudaStream_t st);
+cudaError_t launch_kick_hist(const DeviceState& s, const StepParams& p, cudaStream_t st);
+cudaError_t launch_advance(const DeviceState& s, cudaStream_t st);
+cudaError_t launch_hist_append(const DeviceState& s, cudaStream_t st);
+// single-CTA fused multi-step kernel (faithful arithmetic), n <= kTinyMax
+constexpr int kTinyMax = 512;
+cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long long nsteps, bool detect,
+                              cudaStream_t st);
+cudaError_t launch_pack(double4* pos4, const double* x, const double* y, const double* z, const double* m,
+                        long long n, cudaStream_t st);
+cudaError_t launch_unpack(const double4* pos4, double* x, double* y, double* z, long long n, cudaStream_t st);
+cudaError_t launch_potential(const DeviceState& s, const StepParams& p, bool faithful_order, double* d_out,
+                             cudaStream_t st, int* launches);
+cudaError_t launch_energy_angmom(const DeviceState& s, double* d_out4, cudaStream_t st, int* launches);
+
+// ---- peak.cu ----
+cudaError_t run_fp64_peak(int device, double seconds, double* tflops_best, double* tflops_mean, double* mhz);
+
+}  // namespace orb

@@ -1,0 +1,87 @@
+// peak.cu -- FP64 DFMA-chain microbenchmark: the measured roofline denominator
+// for the force kernel (MEASURED_PEAKS.json has no FP64 figure).
+#include <algorithm>
+#include <vector>
+
+#include "kernels.h"
+
+namespace orb {
+
+constexpr int kChains = 8;
+
+__global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, long long iters, double a, double b,
+                                                         long long* cycles) {
+    double r[kChains];
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) r[k] = (double)(threadIdx.x + k) * 1e-3;
+    const long long c0 = clock64();
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int k = 0; k < kChains; ++k) r[k] = fma(r[k], a, b);
+        }
+    }
+    const long long c1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) s += r[k];
+    out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = c1 - c0;
+}
+
+cudaError_t run_fp64_peak(int device, double seconds, double* tflops_best, double* tflops_mean, double* mhz) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return e;
+    const int block = 256;
+    const int grid = prop.multiProcessorCount * 4;       // 32 warps/SM: saturates the FP64 pipe
+    const long long iters = 4096;                        // x 64 DFMA per thread per iteration
+    double* d_out = nullptr;
+    long long* d_cyc = nullptr;
+    if ((e = cudaMalloc(&d_out, sizeof(double) * grid * block)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d_cyc, sizeof(long long))) != cudaSuccess) { cudaFree(d_out); return e; }
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    const double flops = 2.0 * (double)grid * block * (double)iters * 8.0 * kChains;
+    std::vector<double> tf;
+    std::vector<double> clk;
+    // warm-up
+    for (int w = 0; w < 3; ++w) dfma_chain_kernel<<<grid, block, 0, st>>>(d_out, iters, 0.999999, 1e-9, d_cyc);
+    cudaStreamSynchronize(st);
+    double elapsed = 0.0;
+    while (elapsed < seconds * 1e3 || tf.size() < 4) {
+        cudaEventRecord(ev0, st);
+        dfma_chain_kernel<<<grid, block, 0, st>>>(d_out, iters, 0.999999, 1e-9, d_cyc);
+        cudaEventRecord(ev1, st);
+        if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        long long cyc = 0;
+        cudaMemcpy(&cyc, d_cyc, sizeof cyc, cudaMemcpyDeviceToHost);
+        tf.push_back(flops / (ms * 1e-3) / 1e12);
+        clk.push_back((double)cyc / (ms * 1e-3) / 1e6);
+        elapsed += ms;
+        if (tf.size() > 100000) break;
+    }
+    if (e == cudaSuccess && !tf.empty()) {
+        *tflops_best = *std::max_element(tf.begin(), tf.end());
+        double s = 0.0, c = 0.0;
+        const size_t half = tf.size() / 2;
+        for (size_t k = half; k < tf.size(); ++k) { s += tf[k]; c += clk[k]; }
+        *tflops_mean = s / (double)(tf.size() - half);
+        *mhz = c / (double)(tf.size() - half);
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaStreamDestroy(st);
+    cudaFree(d_out);
+    cudaFree(d_cyc);
+    return e;
+}
+
+}  // namespace orb

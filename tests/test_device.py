@@ -1,0 +1,353 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI, against the oracle.
+
+All tests here need a B200 (`-m gpu`).  Oracle: oracle/nbody_oracle.c (pinned
+bit-exact to the reference in tests/test_oracle.py).  Bars:
+  faithful mode: bit-exact accelerations / state (reference core/physics.py:125-159, engine.py:65-97)
+  fast mode:     relative acceleration error <= 1e-12 per step (BASELINE.json north_star)
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = 6.67430e-11
+TOL_FAST = 1e-12          # BASELINE.json: relative acceleration error <= 1e-12 per step
+
+
+def bits(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64)).view(np.uint64)
+
+
+def assert_bits(a, b, what=""):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    same = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
+    if not same.all():
+        rel = np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+        raise AssertionError(f"{what}: {np.count_nonzero(~same)}/{same.size} differ, max rel {rel:.3e}")
+
+
+def relerr(a, ref):
+    return np.linalg.norm(a - ref, axis=1) / np.linalg.norm(ref, axis=1)
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from core import _native
+    assert _native.device_count() > 0
+    return _native
+
+
+def device_accel(nat, c, mode, eps=None):
+    dev = nat.DeviceSystem(c.n, 0, mode)
+    dev.set_params(c["dt"], c["eps"] if eps is None else eps, G)
+    dev.upload(*c.arrays())
+    dev.accel()
+    a = dev.download_acc().T.copy()
+    return dev, a
+
+
+def test_device_info(nat):
+    info = nat.device_info(0)
+    assert info["cc"][0] >= 10 and info["sm_count"] >= 100
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 9, 15, 26, 33, 64, 257, 513, 1024, 4096])
+def test_force_faithful_bit_exact(nat, orc, n):
+    """pairwise_accelerations vs GPU on random clouds."""
+    from core import synthetic
+    c = synthetic.random_cloud(n, seed=1000 + n)
+    for eps in (c["eps"], 0.0):
+        dev, a = device_accel(nat, c, nat.MODE_FAITHFUL, eps)
+        ref, U = orc.pairwise(c["x"], c["y"], c["z"], c["m"], eps, G, nthreads=1)
+        assert_bits(a, ref, f"n={n} eps={eps}")
+        if n > 1:
+            assert_bits(dev.potential(), U, f"U n={n}")
+        dev.close()
+
+
+def test_force_golden_vectors_direct(nat, golden):
+    """The reference's own outputs (no oracle in between)."""
+    from core import synthetic
+    g = golden("force_random")
+    for k in range(int(g["ncases"])):
+        c = synthetic._cloud(np.stack([g[f"c{k}_x"], g[f"c{k}_y"], g[f"c{k}_z"]], 1), np.zeros((len(g[f"c{k}_x"]), 3)),
+                             g[f"c{k}_m"], 0.0, dt=1.0, eps=float(g[f"c{k}_eps"]))
+        dev, a = device_accel(nat, c, nat.MODE_FAITHFUL)
+        assert_bits(a, g[f"c{k}_acc"], f"golden case {k}")
+        assert_bits(dev.potential(), g[f"c{k}_U"], f"golden U {k}")
+        dev.close()
+    # coincident bodies: finite with softening, inf/nan (no exception) without
+    c = synthetic._cloud(np.stack([g["coinc_x"], g["coinc_y"], g["coinc_z"]], 1), np.zeros((5, 3)), g["coinc_m"], 0.0,
+                         dt=1.0, eps=float(g["coinc_soft_eps"]))
+    dev, a = device_accel(nat, c, nat.MODE_FAITHFUL)
+    assert_bits(a, g["coinc_soft_acc"]); dev.close()
+    dev, a = device_accel(nat, c, nat.MODE_FAITHFUL, eps=0.0)
+    assert_bits(a, g["coinc_hard_acc"]); dev.close()
+    dev, a = device_accel(nat, c, nat.MODE_FAST, eps=0.0)
+    assert np.isfinite(a).all() == np.isfinite(g["coinc_hard_acc"]).all() or not np.isfinite(a).all()
+    dev.close()
+
+
+@pytest.mark.parametrize("n", [2, 31, 64, 1000, 4096, 20000])
+@pytest.mark.parametrize("ti", ["1", "2", "4", "6", "8", None])
+def test_force_fast_within_tolerance(nat, orc, n, ti, monkeypatch):
+    from core import synthetic
+    if ti is None:
+        monkeypatch.delenv("ORBITAL_B200_TI", raising=False)
+    else:
+        monkeypatch.setenv("ORBITAL_B200_TI", ti)
+    c = synthetic.random_cloud(n, seed=2000 + n)
+    dev, a = device_accel(nat, c, nat.MODE_FAST)
+    rows = np.arange(n, dtype=np.int64) if n <= 4096 else np.arange(0, n, 37, dtype=np.int64)
+    ref = orc.pairwise_sample(c["x"], c["y"], c["z"], c["m"], c["eps"], G, rows)
+    err = relerr(a[rows], ref)
+    assert err.max() <= TOL_FAST, f"n={n} ti={ti}: max rel err {err.max():.3e}"
+    dev.close()
+
+
+@pytest.mark.parametrize("slabs", ["1", "3", "7"])
+def test_force_fast_slab_decomposition_is_deterministic(nat, slabs, monkeypatch):
+    from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_SLABS", slabs)
+    c = synthetic.plummer(6000, seed=5)
+    dev, a1 = device_accel(nat, c, nat.MODE_FAST)
+    dev.accel()
+    a2 = dev.download_acc().T
+    assert_bits(a1, a2, "run-to-run")
+    dev.close()
+
+
+def test_force_fast_plummer_262144_sampled_rows(nat, orc):
+    """BASELINE config C2 at full size: sampled-row oracle + long-double yardstick + Newton's third law."""
+    from core import synthetic
+    c = synthetic.plummer(262144)
+    dev, a = device_accel(nat, c, nat.MODE_FAST)
+    rng = np.random.default_rng(0)
+    r = np.sqrt(c["x"] ** 2 + c["y"] ** 2 + c["z"] ** 2)
+    rows = np.unique(np.concatenate([rng.choice(c.n, 240, replace=False), np.argsort(r)[:16]])).astype(np.int64)
+    ref = orc.pairwise_sample(c["x"], c["y"], c["z"], c["m"], c["eps"], G, rows)
+    ld, sum_abs = orc.pairwise_sample(c["x"], c["y"], c["z"], c["m"], c["eps"], G, rows, long_double=True)
+    err_ref = relerr(a[rows], ref)
+    err_ld = relerr(a[rows], ld)
+    cond = np.linalg.norm(a[rows] - ld, axis=1) / sum_abs
+    print(f"\nN=262144 fast kernel: vs reference-order fp64 max {err_ref.max():.2e} median {np.median(err_ref):.2e}; "
+          f"vs long double max {err_ld.max():.2e}; |da|/sum|a_ij| max {cond.max():.2e}")
+    assert err_ref.max() <= TOL_FAST and err_ld.max() <= TOL_FAST
+    # size-independent property: total force vanishes (sum m_i a_i = 0) to rounding
+    F = (c["m"][:, None] * a).sum(0)
+    scale = (c["m"] * np.linalg.norm(a, axis=1)).sum()
+    assert np.linalg.norm(F) <= 1e-11 * scale
+    dev.close()
+
+
+@pytest.mark.parametrize("n", [600, 1500])
+def test_step_faithful_kernel_sequence_bit_exact(nat, orc, n):
+    """n > 512 takes the multi-kernel CUDA-graph path; n = 600 also has radii -> overlap detection on."""
+    from core import synthetic
+    from oracle.c_oracle import State
+    c = synthetic.random_cloud(n, seed=n, radius=(1e3 if n == 600 else 0.0))
+    f32 = (np.arange(n) % 2).astype(np.uint8)
+    dev = nat.DeviceSystem(n, 0, nat.MODE_FAITHFUL)
+    dev.set_params(c["dt"], c["eps"], G)
+    dev.set_history(8)
+    vel = [np.where(f32 == 1, v.astype(np.float32).astype(np.float64), v) for v in (c["vx"], c["vy"], c["vz"])]
+    dev.upload(c["x"], c["y"], c["z"], *vel, c["m"], c["radius"], f32)
+    dev.accel()
+    dev.history_append()
+    st = State(orc, *c.arrays(), f32, c["dt"], c["eps"])
+    for k in (1, 3, 20):
+        done, nov = dev.step(k)
+        assert (done, nov) == (k, 0)
+        st.step(k, collisions=False)
+        s = dev.download_state()
+        assert_bits(np.stack([s["x"], s["y"], s["z"]], 1), st.pos, f"pos after +{k}")
+        assert_bits(np.stack([s["vx"], s["vy"], s["vz"]], 1), st.vel, f"vel after +{k}")
+        assert_bits(dev.download_acc().T, st.acc, f"acc after +{k}")
+    assert dev.history_count() == 25
+    h = dev.history_download(8)
+    assert h.shape == (8, n, 3)
+    assert_bits(h[-1], st.pos, "last ring entry")
+    assert dev.launch_count() > 24 * 4
+    dev.close()
+
+
+def test_disk4096_matches_reference_engine(nat, golden):
+    """BASELINE config C1: the real reference's ctor + 2 steps at N=4096 (fixture) vs the faithful GPU path."""
+    from core import synthetic
+    g = golden("disk4096_f32")
+    c = synthetic.uniform_disk(4096)
+    dev = nat.DeviceSystem(4096, 0, nat.MODE_FAITHFUL)
+    dev.set_params(c["dt"], c["eps"], G)
+    vel = [v.astype(np.float32).astype(np.float64) for v in (c["vx"], c["vy"], c["vz"])]
+    dev.upload(c["x"], c["y"], c["z"], *vel, c["m"], c["radius"], np.ones(4096, np.uint8))
+    dev.accel()
+    assert_bits(dev.download_acc().T, g["acc_0"], "ctor acc")
+    assert_bits(dev.potential(), g["U_0"], "ctor U")
+    for s in (1, 2):
+        assert dev.step(1) == (1, 0)
+        st = dev.download_state()
+        assert_bits(np.stack([st["x"], st["y"], st["z"]], 1), g[f"pos_{s}"], f"pos {s}")
+        assert_bits(np.stack([st["vx"], st["vy"], st["vz"]], 1), g[f"vel_{s}"], f"vel {s}")
+        assert_bits(dev.download_acc().T, g[f"acc_{s}"], f"acc {s}")
+        assert_bits(dev.potential(), g[f"U_{s}"], f"U {s}")
+    # fast mode on the same steps: <= 1e-12 relative acceleration error per step
+    fast = nat.DeviceSystem(4096, 0, nat.MODE_FAST)
+    fast.set_params(c["dt"], c["eps"], G)
+    fast.upload(c["x"], c["y"], c["z"], *vel, c["m"], c["radius"], np.ones(4096, np.uint8))
+    fast.accel()
+    assert relerr(fast.download_acc().T, g["acc_0"]).max() <= TOL_FAST
+    assert fast.step(2) == (2, 0)
+    assert relerr(fast.download_acc().T, g["acc_2"]).max() <= 1e-9     # trajectories have diverged by ~1 ulp of state
+    sf = fast.download_state()
+    dpos = np.linalg.norm(np.stack([sf["x"], sf["y"], sf["z"]], 1) - g["pos_2"], axis=1)
+    assert (dpos[1:] / np.linalg.norm(g["pos_2"][1:], axis=1)).max() <= 1e-12
+    assert abs(fast.potential() - float(g["U_2"])) <= 1e-12 * abs(float(g["U_2"]))
+    dev.close(); fast.close()
+
+
+@pytest.mark.parametrize("mode_name", ["faithful", "fast"])
+@pytest.mark.parametrize("n", [24, 700])
+def test_overlap_detection_matches_exact_test(nat, mode_name, n):
+    """Fused detection (physics.py:517-518): the flagged pair set equals the exact host test; device halts."""
+    rng = np.random.default_rng(n)
+    box = 4e4 if n == 24 else 3e5
+    x, y, z = (rng.uniform(-box, box, n) for _ in range(3))
+    v = rng.standard_normal((3, n)) * 50
+    m = np.exp(rng.uniform(np.log(1e14), np.log(1e16), n))
+    radius = rng.uniform(2e3, 8e3, n)
+    mode = nat.MODE_FAITHFUL if mode_name == "faithful" else nat.MODE_FAST
+    dev = nat.DeviceSystem(n, 0, mode)
+    dev.set_params(2.0, 10.0, G)
+    dev.set_history(4)
+    dev.upload(x, y, z, v[0], v[1], v[2], m, radius)
+    dev.accel()
+    dev.history_append()
+    done, nov = dev.step(5)
+    assert done == 1 and nov > 0, "device must halt after the first overlapping step"
+    assert dev.history_count() == 1, "the halting step's snapshot is appended by the host after resolution"
+    s = dev.download_state()
+    P = np.stack([s["x"], s["y"], s["z"]], 1)
+    want = {(i, j) for i in range(n) for j in range(i + 1, n)
+            if np.linalg.norm(P[i] - P[j]) <= radius[i] + radius[j]}
+    pairs, count = dev.overlap_pairs()
+    got = {tuple(p) for p in pairs.tolist()}
+    assert count == len(pairs) == nov
+    assert got == want, f"{len(got ^ want)} pairs differ"
+    # after 'resolution' (here: shrink the radii) the run resumes
+    dev.upload(s["x"], s["y"], s["z"], s["vx"], s["vy"], s["vz"], m, np.full(n, 1e-3))
+    dev.history_append()
+    assert dev.step(4) == (4, 0)
+    assert dev.history_count() == 6
+    dev.close()
+
+
+def test_engine_fast_mode_collisions_close_to_reference(golden):
+    """Fast-mode engine with contacts: same contact sequence, state within 1e-9 of the reference run."""
+    from tests.test_engine import build_engine, state_of
+    g = golden("coll_dense_f32")
+    eng = build_engine(g, mode="fast")
+    eng.run(30)
+    p, v, _ = state_of(eng)
+    assert np.abs(p - g["pos_30"]).max() <= 1e-9 * np.abs(g["pos_30"]).max()
+    assert np.abs(v - g["vel_30"]).max() <= 1e-6 * np.abs(g["vel_30"]).max()
+
+
+def test_ensemble_faithful_bit_exact_and_fast_close(nat, orc):
+    """BASELINE config C3 (small batch): every system == a standalone reference engine on its 16 bodies."""
+    from core import synthetic
+    from core.ensemble import EnsembleEngine
+    e = synthetic.ensemble(48, 16)
+    K = 200
+    for vel_f32 in (False, True):
+        want = {k: np.array(e[k], dtype=np.float64, copy=True) for k in ("x", "y", "z", "vx", "vy", "vz")}
+        if vel_f32:
+            for k in ("vx", "vy", "vz"):
+                want[k] = want[k].astype(np.float32).astype(np.float64)
+        orc.lib.orc_ensemble_step(48, 16, want["x"].reshape(-1), want["y"].reshape(-1), want["z"].reshape(-1),
+                                  want["vx"].reshape(-1), want["vy"].reshape(-1), want["vz"].reshape(-1),
+                                  np.ascontiguousarray(e["m"]).reshape(-1), e["dt"], e["eps"], G, K, int(vel_f32), 0)
+        for fused in (True, False):
+            ens = EnsembleEngine(*(e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")), dt=e["dt"],
+                                 softening=e["eps"], mode="faithful", vel_f32=vel_f32)
+            if fused:
+                ens.step(K, fused=True)
+            else:
+                ens.step(K // 2, fused=False); ens.step(K - K // 2, fused=True)
+            got = ens.state()
+            for k in want:
+                assert_bits(got[k], want[k], f"ensemble {k} vel_f32={vel_f32} fused={fused}")
+            ens.close()
+    fast = EnsembleEngine(*(e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")), dt=e["dt"], softening=e["eps"],
+                          mode="fast")
+    E0 = fast.energy()
+    fast.step(K, fused=True)
+    got = fast.state()
+    ref64 = {k: np.array(e[k], dtype=np.float64, copy=True) for k in ("x", "y", "z", "vx", "vy", "vz")}
+    orc.lib.orc_ensemble_step(48, 16, *(ref64[k].reshape(-1) for k in ("x", "y", "z", "vx", "vy", "vz")),
+                              np.ascontiguousarray(e["m"]).reshape(-1), e["dt"], e["eps"], G, K, 0, 0)
+    num = np.sqrt(sum((got[k] - ref64[k]) ** 2 for k in ("x", "y", "z")))
+    den = np.sqrt(sum(ref64[k] ** 2 for k in ("x", "y", "z")))
+    assert (num[:, 1:] / den[:, 1:]).max() <= 1e-9, "fast ensemble trajectory divergence after 200 steps"
+    E1 = fast.energy()
+    assert np.abs((E1 - E0) / E0).max() < 1e-3
+    fast.close()
+
+
+def test_ensemble_odd_sizes(nat, orc):
+    from core import synthetic
+    from core.ensemble import EnsembleEngine
+    for nb in (2, 5, 9, 32):
+        e = synthetic.ensemble(7, nb)
+        args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
+        ref = {k: np.array(e[k], dtype=np.float64, copy=True) for k in ("x", "y", "z", "vx", "vy", "vz")}
+        orc.lib.orc_ensemble_step(7, nb, *(ref[k].reshape(-1) for k in ("x", "y", "z", "vx", "vy", "vz")),
+                                  np.ascontiguousarray(e["m"]).reshape(-1), e["dt"], e["eps"], G, 10, 0, 0)
+        f = EnsembleEngine(*args, dt=e["dt"], softening=e["eps"], mode="faithful"); f.step(10)
+        for k in ref:
+            assert_bits(f.state()[k], ref[k], f"nb={nb} {k}")
+        q = EnsembleEngine(*args, dt=e["dt"], softening=e["eps"], mode="fast"); q.step(10)
+        assert np.abs(q.state()["x"] - ref["x"]).max() <= 1e-10 * np.abs(ref["x"]).max()
+        f.close(); q.close()
+
+
+def test_pairwise_accelerations_operator(golden):
+    """The narrow operator seam: same signature / return types as the reference function."""
+    from core.physics import Coordinates, Object, pairwise_accelerations
+    g = golden("force_random")
+    k = 5
+    objs = [Object(float(g[f"c{k}_m"][i]), 0.0, None,
+                   Coordinates(float(g[f"c{k}_x"][i]), float(g[f"c{k}_y"][i]), float(g[f"c{k}_z"][i])))
+            for i in range(len(g[f"c{k}_m"]))]
+    acc, U = pairwise_accelerations(objs, eps=float(g[f"c{k}_eps"]))
+    assert set(acc) == {o.uuid for o in objs} and acc[objs[0].uuid].shape == (3,)
+    assert_bits(np.array([acc[o.uuid] for o in objs]), g[f"c{k}_acc"])
+    assert_bits(U, g[f"c{k}_U"])
+    acc_f, U_f = pairwise_accelerations(objs, eps=float(g[f"c{k}_eps"]), mode="fast")
+    assert relerr(np.array([acc_f[o.uuid] for o in objs]), g[f"c{k}_acc"]).max() <= TOL_FAST
+    assert abs(U_f - U) <= 1e-13 * abs(U)
+
+
+def test_diagnostics_device_reductions(nat, orc):
+    from core import synthetic
+    c = synthetic.plummer(30000, seed=3)
+    dev = nat.DeviceSystem(c.n, 0, nat.MODE_FAST)
+    dev.set_params(c["dt"], c["eps"], G)
+    dev.upload(*c.arrays())
+    K, L = dev.energy_angmom()
+    K_ref = float(np.sum(0.5 * c["m"] * (c["vx"] ** 2 + c["vy"] ** 2 + c["vz"] ** 2)))
+    assert abs(K - K_ref) <= 1e-12 * K_ref
+    pos = np.stack([c["x"], c["y"], c["z"]], 1); mom = c["m"][:, None] * np.stack([c["vx"], c["vy"], c["vz"]], 1)
+    L_ref = np.cross(pos, mom).sum(0)
+    assert np.linalg.norm(L - L_ref) <= 1e-10 * np.abs(np.cross(pos, mom)).sum()
+    U = dev.potential()
+    U_ref = orc.potential(c["x"], c["y"], c["z"], c["m"], c["eps"], G)
+    assert abs(U - U_ref) <= 1e-12 * abs(U_ref)
+    dev.close()
+
+
+def test_fp64_peak_microbenchmark(nat):
+    p = nat.fp64_peak(0, 0.3)
+    print(f"\nFP64 DFMA peak: best {p['tflops_best']:.2f} TF, mean {p['tflops_mean']:.2f} TF at {p['sm_clock_mhz']:.0f} MHz")
+    assert 10.0 < p["tflops_best"] < 60.0
