@@ -85,7 +85,8 @@ int orb_set_mode(orb_engine* e, int mode);
 /* Device ring of the last `capacity` position snapshots (engine.history, core/engine.py:34,88-92).
  * 0 disables recording. Resets the ring. */
 int orb_set_history(orb_engine* e, int64_t capacity);
-/* Run on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream. NULL = own stream. */
+/* Run on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream. NULL = the handle's
+ * own stream; pass cudaStreamLegacy (0x1) for the legacy default stream. */
 int orb_set_stream(orb_engine* e, void* cuda_stream);
 
 /* ---- state transfer ----------------------------------------------------

@@ -144,6 +144,15 @@ def _ptr(a):
     return a.ctypes.data_as(_vp)
 
 
+_CUDA_STREAM_LEGACY = 0x1     # cudaStreamLegacy: the explicit handle of the NULL stream
+
+
+def _stream_arg(cuda_stream):
+    if cuda_stream is None:
+        return None                     # NULL -> the library's own stream
+    return _vp(int(cuda_stream) or _CUDA_STREAM_LEGACY)
+
+
 def _c64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -222,7 +231,8 @@ class DeviceSystem:
         check(lib().orb_set_history(self._h, int(capacity)))
 
     def set_stream(self, cuda_stream: int | None):
-        check(lib().orb_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+        """None: the handle's own stream. An integer cudaStream_t; 0 means the legacy default stream."""
+        check(lib().orb_set_stream(self._h, _stream_arg(cuda_stream)))
 
     # -- transfers ---------------------------------------------------------
     def upload(self, x, y, z, vx, vy, vz, m, radius, vel_is_f32=None):
@@ -360,7 +370,7 @@ class DeviceEnsemble:
         check(lib().orb_ens_set_params(self._h, float(dt), float(eps), float(G)))
 
     def set_stream(self, cuda_stream):
-        check(lib().orb_ens_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+        check(lib().orb_ens_set_stream(self._h, _stream_arg(cuda_stream)))
 
     def upload(self, x, y, z, vx, vy, vz, m):
         arrs = [_c64(a) for a in (x, y, z, vx, vy, vz, m)]

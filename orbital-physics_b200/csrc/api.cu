@@ -444,7 +444,15 @@ int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_over
         if (use_tiny(e)) {
             CU(launch_tiny_steps(e->s, e->p, nsteps, e->detect, st));
             ++e->launches;
-        } else if (nsteps == 1) {
+        } else if (nsteps == 1 || st == cudaStreamLegacy || st == nullptr) {
+            // (stream capture is not available on the legacy default stream)
+            for (int64_t k = 0; k < nsteps; ++k) {
+                int launches = 0;
+                int rc = enqueue_step(e, &launches);
+                e->launches += launches;
+                if (rc) return rc;
+            }
+        } else if (false) {
             int launches = 0;
             int rc = enqueue_step(e, &launches);
             e->launches += launches;

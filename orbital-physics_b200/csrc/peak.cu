@@ -9,8 +9,15 @@ namespace orb {
 
 constexpr int kChains = 8;
 
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+
+// stamps: per block {smid, start clock, end clock}; clocks of one SM share a counter
 __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, long long iters, double a, double b,
-                                                         long long* cycles) {
+                                                         long long* stamps) {
     double r[kChains];
 #pragma unroll
     for (int k = 0; k < kChains; ++k) r[k] = (double)(threadIdx.x + k) * 1e-3;
@@ -27,7 +34,11 @@ __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, long long 
 #pragma unroll
     for (int k = 0; k < kChains; ++k) s += r[k];
     out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = s;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = c1 - c0;
+    if (threadIdx.x == 0) {
+        stamps[3 * blockIdx.x] = smid();
+        stamps[3 * blockIdx.x + 1] = c0;
+        stamps[3 * blockIdx.x + 2] = c1;
+    }
 }
 
 cudaError_t run_fp64_peak(int device, double seconds, double* tflops_best, double* tflops_mean, double* mhz) {
@@ -41,7 +52,7 @@ cudaError_t run_fp64_peak(int device, double seconds, double* tflops_best, doubl
     double* d_out = nullptr;
     long long* d_cyc = nullptr;
     if ((e = cudaMalloc(&d_out, sizeof(double) * grid * block)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&d_cyc, sizeof(long long))) != cudaSuccess) { cudaFree(d_out); return e; }
+    if ((e = cudaMalloc(&d_cyc, sizeof(long long) * 3 * grid)) != cudaSuccess) { cudaFree(d_out); return e; }
     cudaStream_t st;
     cudaStreamCreate(&st);
     cudaEvent_t ev0, ev1;
@@ -61,8 +72,18 @@ cudaError_t run_fp64_peak(int device, double seconds, double* tflops_best, doubl
         if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) break;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
-        long long cyc = 0;
-        cudaMemcpy(&cyc, d_cyc, sizeof cyc, cudaMemcpyDeviceToHost);
+        std::vector<long long> stamps(3 * (size_t)grid);
+        cudaMemcpy(stamps.data(), d_cyc, sizeof(long long) * 3 * grid, cudaMemcpyDeviceToHost);
+        // busy span of the first SM seen: max(end) - min(start) over its blocks
+        long long lo = 0, hi = 0;
+        bool first = true;
+        for (int b = 0; b < grid; ++b) {
+            if (stamps[3 * b] != stamps[0]) continue;
+            if (first) { lo = stamps[3 * b + 1]; hi = stamps[3 * b + 2]; first = false; }
+            lo = std::min(lo, stamps[3 * b + 1]);
+            hi = std::max(hi, stamps[3 * b + 2]);
+        }
+        const long long cyc = hi - lo;
         tf.push_back(flops / (ms * 1e-3) / 1e12);
         clk.push_back((double)cyc / (ms * 1e-3) / 1e6);
         elapsed += ms;
