@@ -48,17 +48,21 @@ class ShardedSystem:
         self.n = int(np.asarray(x).shape[0])
         self.lo, self.hi = slab(self.n, self.world, self.rank)
         self.device = self.rank % max(1, _native.device_count()) if device is None else int(device)
-        self.dev = _native.DeviceSystem(self.n, self.device, mode, self.lo, self.hi)
+        self.dev = self._make_device(mode)
         self.dev.set_params(dt, eps, G)
         self.dev.upload(x, y, z, vx, vy, vz, m, radius, vel_is_f32)
-        self._pos4 = self._wrap(self.dev.pos4_ptr(), (self.n, 4))
-        self._vel = self._wrap(self.dev.vel_ptr(), (3, self.n))
+        self._pos4 = self._view("pos4", (self.n, 4))
+        self._vel = self._view("vel", (3, self.n))
         self._bind_stream()
         self.dev.accel()                      # engine.py:41 -- local targets vs all sources
         self.steps_done = 0
 
     # -- backend seams (overridden by the CPU test double) ------------------
-    def _wrap(self, ptr, shape):
+    def _make_device(self, mode):
+        return _native.DeviceSystem(self.n, self.device, mode, self.lo, self.hi)
+
+    def _view(self, which, shape):
+        ptr = self.dev.pos4_ptr() if which == "pos4" else self.dev.vel_ptr()
         return self.torch.as_tensor(_CudaView(ptr, shape), device=f"cuda:{self.device}")
 
     def _bind_stream(self):

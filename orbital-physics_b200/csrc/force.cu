@@ -279,7 +279,9 @@ FastPlan plan_fast(long long n_tgt, long long n_src, int sm_count) {
     FastPlan p;
     const char* env_ti = getenv("ORBITAL_B200_TI");
     const long long per_sm = (n_tgt + sm_count - 1) / sm_count;
-    int ti = per_sm >= 4 * 128 * 4 ? 4 : (per_sm >= 2 * 128 * 2 ? 2 : 1);
+    // measured on B200 at N=262144 (profiles/r1_sweep.txt): TI=8 61.7 %, 6 60.8 %, 4 59.7 %, 2 57.4 %, 1 55.7 % of
+    // the DFMA peak -- more targets per thread amortise the LDS/MUFU/issue overhead of each source.
+    int ti = per_sm >= 1024 ? 8 : (per_sm >= 256 ? 4 : (per_sm >= 64 ? 2 : 1));
     if (env_ti) {
         const int v = atoi(env_ti);
         if (v == 1 || v == 2 || v == 4 || v == 6 || v == 8) ti = v;

@@ -150,3 +150,71 @@ class FakeDeviceSystem:
         if k <= 0:
             return np.empty((0, self.n, 3))
         return np.stack(self.hist[-k:])
+
+
+class FakeShardedDevice:
+    """CPU stand-in for a *sharded* DeviceSystem (orb_create_sharded / orb_step_begin / orb_step_finish)."""
+
+    def __init__(self, n, device=0, mode=0, tgt_lo=0, tgt_hi=None):
+        self.n, self.lo, self.hi = int(n), int(tgt_lo), int(n if tgt_hi is None else tgt_hi)
+        self.orc = load_c_oracle()
+        self.pos4 = np.zeros((self.n, 4))
+        self.vel = np.zeros((3, self.n))
+        self.acc = np.zeros((3, self.n))
+
+    def close(self):
+        pass
+
+    def set_params(self, dt, eps, G=6.67430e-11):
+        self.dt, self.eps, self.G = float(dt), float(eps), float(G)
+
+    def set_stream(self, s):
+        pass
+
+    def upload(self, x, y, z, vx, vy, vz, m, radius, vel_is_f32=None):
+        self.pos4[:, 0], self.pos4[:, 1], self.pos4[:, 2], self.pos4[:, 3] = x, y, z, m
+        self.vel[0], self.vel[1], self.vel[2] = vx, vy, vz
+        self.f32 = np.zeros(self.n, bool) if vel_is_f32 is None else np.asarray(vel_is_f32, bool)
+
+    def accel(self):
+        rows = np.arange(self.lo, self.hi, dtype=np.int64)
+        p = self.pos4
+        a = self.orc.pairwise_sample(np.ascontiguousarray(p[:, 0]), np.ascontiguousarray(p[:, 1]),
+                                     np.ascontiguousarray(p[:, 2]), np.ascontiguousarray(p[:, 3]),
+                                     self.eps, self.G, rows)
+        self.acc[:, self.lo:self.hi] = a.T
+
+    def _kick(self):
+        s = slice(self.lo, self.hi)
+        h = 0.5 * self.dt
+        v = self.vel[:, s] + h * self.acc[:, s]
+        f = self.f32[s]
+        v[:, f] = v[:, f].astype(np.float32).astype(np.float64)
+        self.vel[:, s] = v
+
+    def step_begin(self):
+        self._kick()
+        s = slice(self.lo, self.hi)
+        f = self.f32[s]
+        v = self.vel[:, s]
+        step = v * self.dt
+        step[:, f] = (v[:, f].astype(np.float32) * np.float32(self.dt)).astype(np.float64)
+        self.pos4[s, :3] = self.pos4[s, :3] + step.T
+
+    def step_finish(self):
+        self.accel()
+        self._kick()
+
+    def synchronize(self):
+        pass
+
+    def download_state(self, out=None):
+        return {"x": self.pos4[:, 0].copy(), "y": self.pos4[:, 1].copy(), "z": self.pos4[:, 2].copy(),
+                "vx": self.vel[0].copy(), "vy": self.vel[1].copy(), "vz": self.vel[2].copy()}
+
+    def energy_angmom(self):
+        s = slice(self.lo, self.hi)
+        m = self.pos4[s, 3]
+        K = float(np.sum(0.5 * m * (self.vel[:, s] ** 2).sum(0)))
+        L = np.cross(self.pos4[s, :3], (m * self.vel[:, s]).T).sum(0)
+        return K, L
