@@ -112,11 +112,18 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(n, cloud, budget_s, nthreads=0):
     """Time the oracle port (reference algorithm, C, all host threads) on a bounded row sample."""
     from oracle import load_c_oracle
     orc = load_c_oracle()
-    threads = orc.max_threads if nthreads <= 0 else nthreads
+    threads = host_threads() if nthreads <= 0 else nthreads
     rng = np.random.default_rng(1)
     probe = rng.choice(n, size=min(n, 64 * threads), replace=False).astype(np.int64)
     t0 = time.perf_counter()
@@ -142,7 +149,7 @@ def run_reference(args):
     cloud = synthetic.plummer(n)
     from oracle import load_c_oracle
     orc = load_c_oracle()
-    threads = orc.max_threads
+    threads = host_threads()          # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     rng = np.random.default_rng(1)
     # calibrate ~3 s of CPU work per step
     probe = rng.choice(n, size=min(n, 32 * threads), replace=False).astype(np.int64)
