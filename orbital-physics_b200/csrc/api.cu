@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -12,6 +13,7 @@
 
 #include "../../include/orbital_b200.h"
 #include "ensemble.h"
+#include "force_sym.h"
 #include "kernels.h"
 
 using namespace orb;
@@ -60,6 +62,8 @@ struct orb_engine {
     StepParams p{};
     FastPlan plan;
     bool plan_valid = false;
+    SymPlan sym;                     // pair-symmetric kernel (unsharded fast mode)
+    bool use_sym = true;
     bool detect = false;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -87,7 +91,15 @@ bool use_tiny(const orb_engine* e) {
     return e->mode == ORB_MODE_FAITHFUL && !e->sharded && e->s.n <= kTinyMax;
 }
 
+bool sym_applicable(const orb_engine* e) {
+    return e->mode == ORB_MODE_FAST && e->use_sym && !e->sharded;
+}
+
 int ensure_plan(orb_engine* e) {
+    if (sym_applicable(e)) {
+        if (!e->sym.valid) CU(plan_sym(e->sym, e->s.n, e->sm_count));
+        return ORB_OK;
+    }
     if (e->mode == ORB_MODE_FAST && !e->plan_valid) {
         e->plan = plan_fast(e->s.tgt_hi - e->s.tgt_lo, e->s.n, e->sm_count);
         const long long need = e->plan.slabs > 1 ? (long long)e->plan.slabs * 3 * (e->s.tgt_hi - e->s.tgt_lo) : 0;
@@ -108,7 +120,10 @@ int enqueue_force(orb_engine* e, bool detect, int* launches) {
     if (e->mode == ORB_MODE_FAST) {
         int rc = ensure_plan(e);
         if (rc) return rc;
-        CU(launch_force_fast(e->s, e->p, e->plan, detect, e->stream, launches));
+        if (sym_applicable(e))
+            CU(launch_force_sym(e->s, e->p, e->sym, detect, e->stream, launches));
+        else
+            CU(launch_force_fast(e->s, e->p, e->plan, detect, e->stream, launches));
     } else {
         CU(launch_force_faithful(e->s, e->p, detect, e->stream, launches));
     }
@@ -169,6 +184,7 @@ int alloc_engine(orb_engine* e) {
 
 void free_engine(orb_engine* e) {
     drop_graphs(e);
+    free_sym(e->sym);
     cudaFree(e->s.pos4); cudaFree(e->s.vel); cudaFree(e->s.acc); cudaFree(e->s.radius); cudaFree(e->s.vf32);
     cudaFree(e->s.ctl); cudaFree(e->s.pairs); cudaFree(e->s.hist); cudaFree(e->s.scratch);
     cudaFree(e->s.reduce_buf); cudaFree(e->d_stage); cudaFree(e->d_diag);
@@ -264,6 +280,10 @@ int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_
     e->s.tgt_lo = tgt_lo;
     e->s.tgt_hi = tgt_hi;
     e->sharded = !(tgt_lo == 0 && tgt_hi == n);
+    {
+        const char* env = getenv("ORBITAL_B200_SYM");     // "0": one-sided fast kernel even when unsharded
+        e->use_sym = !(env && env[0] == '0');
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) {
@@ -562,9 +582,17 @@ int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, in
     } else if (e->mode == ORB_MODE_FAST) {
         int rc = ensure_plan(e);
         if (rc) return rc;
-        nm = fast_kernel_name(e->plan.ti, e->detect);
-        g = e->plan.grid; b = e->plan.block; sm = e->plan.smem;
-        lps = 4 + (e->plan.slabs > 1 ? 1 : 0);
+        if (sym_applicable(e)) {
+            nm = sym_kernel_name(e->sym.ti, e->detect);
+            g = 0;
+            for (const auto& pan : e->sym.panels) g += pan.n_items;
+            b = 128; sm = 0;
+            lps = 3 + 2 * (int)e->sym.panels.size();
+        } else {
+            nm = fast_kernel_name(e->plan.ti, e->detect);
+            g = e->plan.grid; b = e->plan.block; sm = e->plan.smem;
+            lps = 4 + (e->plan.slabs > 1 ? 1 : 0);
+        }
     } else {
         nm = "force_faithful_kernel";
         faithful_geometry(e->s.tgt_hi - e->s.tgt_lo, &g, &b);

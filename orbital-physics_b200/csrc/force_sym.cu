@@ -1,0 +1,412 @@
+// force_sym.cu -- pair-symmetric fast force kernel (sm_100a).
+//
+// Same result as force_fast_kernel (reference core/physics.py:125-159) but each unordered pair
+// (i<j) is evaluated ONCE and applied to both bodies, which is how the reference's half-matrix
+// loop works (physics.py:136-155: a_i += G m_j s d, a_j -= G m_i s d).  FP64-pipe cost per pair:
+//   3 DADD (d) + 3 DFMA (r^2) + 6 (y0^3 (1 + 3/2 e + 15/8 e^2) from the MUFU.RSQ64H seed)
+//   + [1 DMUL + 3 DFMA] for body i + [1 DMUL + 3 DFMA] for body j = 20 per pair
+//   = 10 FP64 instructions per ordered interaction (the one-sided kernel needs 16).
+//
+// Decomposition.  Bodies are cut into I-blocks of 128*TI bodies and tiles of 256 bodies.  A work
+// item (CTA) is (I-block, chunk of consecutive tiles at or after the I-block): the thread keeps TI
+// bodies of the I-block (position, mass, accumulator) in registers; tiles stream through the same
+// 4-stage bulk-TMA ring as the one-sided kernel.
+//   * tiles that overlap the I-block ("diagonal") are processed one-sided with the self-pair masked;
+//   * tiles after it are processed symmetrically with a warp-level systolic rotation: each lane
+//     holds one tile body j and its accumulator; after every TI pairs the 7 doubles of j rotate to
+//     the neighbouring lane (14 SHFL), so after 32 steps every lane's TI bodies have met all 32
+//     bodies of the round and every j accumulator is back in its home lane.  The four warps'
+//     j-accumulators are summed in fixed order through shared memory and written to the partial
+//     plane P_j[I-block][j].
+// A reduction kernel then forms  a[x] = G (sum_chunks P_i[chunk][x] + sum_{I before x} P_j[I][x])
+// in fixed order, so the result is run-to-run deterministic.  P_j is processed in panels of
+// I-blocks to bound its footprint.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "force_common.cuh"
+#include "force_sym.h"
+
+namespace orb {
+
+struct SymArgs {
+    const double4* pos4;
+    const double* radius;
+    const SymItem* items;
+    double* Pi;                // [n_chunks][3][n]
+    double* Pj;                // [panel_blocks][3][n]
+    long long n;
+    int n_tiles;
+    int I_base;                // first I-block of the current panel
+    double eps2;
+    double rmax1, rmax2;
+    long long rmax1_idx;
+    Ctl* ctl;
+    long long* pairs;
+};
+
+// y0^3 (1-e)^(-3/2) without the mass factor: 6 FP64 instructions
+__device__ __forceinline__ double inv_r3_plain(double r2, int& y0_hi) {
+    const double y0 = rsqrt_seed(r2);
+    y0_hi = __double2hiint(y0);
+    const double u = y0 * y0;
+    const double e = fma(-r2, u, 1.0);
+    const double w = y0 * u;
+    const double p = fma(1.875, e, 1.5);
+    const double q = e * p;
+    return fma(w, q, w);
+}
+
+__device__ __forceinline__ double rot1(double v, int src_lane) {
+    return __shfl_sync(0xffffffffu, v, src_lane);
+}
+
+constexpr int kSymSmem = kStages * kTile * 32 + 128 + kFastWarps * 3 * kTile * 8;
+
+template <int TI, bool DETECT>
+__global__ void __launch_bounds__(kFastThreads, (TI >= 6 ? 2 : 3))
+force_sym_kernel(const SymArgs g) {
+    if (g.ctl->halted) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* tiles = reinterpret_cast<double2*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTile * 32);
+    uint64_t* empty = full + kStages;
+    double* slab = reinterpret_cast<double*>(smem_raw + kStages * kTile * 32 + 128);   // [warp][3][kTile]
+
+    const SymItem it = g.items[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int next_lane = (lane + 1) & 31;
+    constexpr long long B = (long long)kFastThreads * TI;
+    const long long i_lo = (long long)it.I * B;
+    const long long i_hi = min(i_lo + B, g.n);
+    const int diag_end = (int)min((long long)g.n_tiles, (i_hi + kTile - 1) / kTile);
+    const int ntiles = it.t1 - it.t0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kFastWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int s = t % kStages;
+        const long long j0 = (long long)(it.t0 + t) * kTile;
+        const int cnt = (int)min((long long)kTile, g.n - j0);
+        const uint32_t bytes = (uint32_t)cnt * 32u;
+        mbar_expect_tx(&full[s], bytes);
+        tma_load_1d(tiles + (size_t)s * kTile * 2, g.pos4 + j0, bytes, &full[s]);
+    };
+    if (tid == 0) {
+        const int pre = min(kStages, ntiles);
+        for (int t = 0; t < pre; ++t) issue(t);
+    }
+
+    double xi[TI], yi[TI], zi[TI], mi[TI], ax[TI], ay[TI], az[TI];
+    long long idx[TI];
+    int maxhi[TI], thr[TI];
+    double Ri[TI];
+#pragma unroll
+    for (int k = 0; k < TI; ++k) {
+        idx[k] = i_lo + (long long)k * kFastThreads + tid;
+        const long long ld = min(idx[k], g.n - 1);          // tail threads shadow the last body with zero mass
+        const double4 p = g.pos4[ld];
+        xi[k] = p.x; yi[k] = p.y; zi[k] = p.z;
+        mi[k] = idx[k] < g.n ? p.w : 0.0;
+        ax[k] = ay[k] = az[k] = 0.0;
+        maxhi[k] = 0;
+        thr[k] = 0x7fffffff;
+        Ri[k] = 0.0;
+        if (DETECT) {
+            Ri[k] = g.radius[ld];
+            const double partner = (ld == g.rmax1_idx) ? g.rmax2 : g.rmax1;
+            const double rs = Ri[k] + partner;
+            const double bound = (1.0 / sqrt(fma(rs, rs, g.eps2))) * (1.0 - 1.52587890625e-05);
+            thr[k] = __double2hiint(bound) - 1;
+        }
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kStages;
+        mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
+        const double2* tile = tiles + (size_t)s * kTile * 2;
+        const int tile_index = it.t0 + t;
+        const long long j0 = (long long)tile_index * kTile;
+        const int cnt = (int)min((long long)kTile, g.n - j0);
+
+        if (tile_index < diag_end) {
+            // ---- diagonal tile: one-sided, self-pair masked (both directions are evaluated by their owners)
+            tile_loop<TI, DETECT, true>(tile, cnt, j0, g.eps2, xi, yi, zi, idx, ax, ay, az, maxhi);
+        } else {
+            // ---- symmetric tile: systolic rotation, 32 bodies per round
+            const int rounds = (cnt + 31) >> 5;
+            for (int r = 0; r < rounds; ++r) {
+                const int slot = (r << 5) + lane;
+                const bool valid = slot < cnt;
+                const int src = valid ? slot : cnt - 1;       // padded lanes: a real position with zero mass
+                const double2 pa = tile[2 * src];
+                const double2 pb = tile[2 * src + 1];
+                double jx = pa.x, jy = pa.y, jz = pb.x;
+                double jm = valid ? pb.y : 0.0;
+                double bx = 0.0, by = 0.0, bz = 0.0;
+#pragma unroll 2
+                for (int st = 0; st < 32; ++st) {
+#pragma unroll
+                    for (int k = 0; k < TI; ++k) {
+                        const double dx = jx - xi[k];
+                        const double dy = jy - yi[k];
+                        const double dz = jz - zi[k];
+                        const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, g.eps2)));
+                        int hi;
+                        const double s0 = inv_r3_plain(r2, hi);
+                        if (DETECT) maxhi[k] = max(maxhi[k], hi);
+                        const double si = s0 * jm;            // physics.py:151  a_i += (G m_j / r^3) d
+                        const double sj = s0 * mi[k];         // physics.py:152  a_j -= (G m_i / r^3) d
+                        ax[k] = fma(si, dx, ax[k]);
+                        ay[k] = fma(si, dy, ay[k]);
+                        az[k] = fma(si, dz, az[k]);
+                        bx = fma(-sj, dx, bx);
+                        by = fma(-sj, dy, by);
+                        bz = fma(-sj, dz, bz);
+                    }
+                    jx = rot1(jx, next_lane); jy = rot1(jy, next_lane); jz = rot1(jz, next_lane);
+                    jm = rot1(jm, next_lane);
+                    bx = rot1(bx, next_lane); by = rot1(by, next_lane); bz = rot1(bz, next_lane);
+                }
+                // 32 rotations: every accumulator is back in its home lane
+                double* mine = slab + (size_t)warp * 3 * kTile;
+                mine[slot] = bx;
+                mine[kTile + slot] = by;
+                mine[2 * kTile + slot] = bz;
+            }
+        }
+        if (DETECT) {
+#pragma unroll
+            for (int k = 0; k < TI; ++k) {
+                if (maxhi[k] >= thr[k] && idx[k] < g.n)
+                    rescan_tile(tile, cnt, j0, idx[k], xi[k], yi[k], zi[k], Ri[k], g.radius, g.ctl, g.pairs);
+                maxhi[k] = 0;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (tile_index >= diag_end) {
+            __syncthreads();
+            // fixed-order sum of the four warps' contributions to the tile bodies -> P_j[I][j]
+            double* out = g.Pj + (long long)(it.I - g.I_base) * 3 * g.n + j0;
+            for (int e = tid; e < 3 * kTile; e += kFastThreads) {
+                const int c = e / kTile;
+                const int slot = e - c * kTile;
+                if (slot < cnt) {
+                    double v = slab[c * kTile + slot];
+#pragma unroll
+                    for (int w = 1; w < kFastWarps; ++w) v += slab[(w * 3 + c) * kTile + slot];
+                    out[(long long)c * g.n + slot] = v;
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0 && t >= 1 && (t - 1 + kStages) < ntiles) {
+            const int tp = t - 1;
+            mbar_wait(&empty[tp % kStages], (uint32_t)((tp / kStages) & 1));
+            issue(tp + kStages);
+        }
+    }
+
+    double* pi = g.Pi + (long long)it.chunk * 3 * g.n;
+#pragma unroll
+    for (int k = 0; k < TI; ++k) {
+        if (idx[k] < g.n) {
+            pi[idx[k]] = ax[k];
+            pi[g.n + idx[k]] = ay[k];
+            pi[2 * g.n + idx[k]] = az[k];
+        }
+    }
+}
+
+// a[x] (+)= G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{I-blocks of this panel before x} P_j[I][x] )
+__global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restrict__ Pi, const double* __restrict__ Pj,
+                                                         double* acc, long long n, long long B, int chunk_tiles,
+                                                         int n_chunks, int I_base, int I_end, double G,
+                                                         int accumulate, const Ctl* ctl) {
+    if (ctl->halted) return;
+    const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const long long X = x / B;
+    const long long T = x / kTile;
+    double s[3] = {0.0, 0.0, 0.0};
+    if (X >= I_base && X < I_end) {
+        const int c_first = (int)(((X * B) / kTile) / chunk_tiles);
+        for (int c = c_first; c < n_chunks; ++c) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s[k] += Pi[((long long)c * 3 + k) * n + x];
+        }
+    }
+    const long long nI = min((T * kTile) / B, (long long)I_end);
+    for (long long I = I_base; I < nI; ++I) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s[k] += Pj[((I - I_base) * 3 + k) * n + x];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double v = G * s[k];
+        acc[x + k * n] = accumulate ? acc[x + k * n] + v : v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int TI, bool DETECT>
+static int sym_occupancy() {
+    int nb = 0;
+    auto kern = force_sym_kernel<TI, DETECT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymSmem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kFastThreads, kSymSmem) != cudaSuccess) nb = 0;
+    return nb;
+}
+
+template <int TI, bool DETECT>
+static cudaError_t launch_sym_t(const SymArgs& a, int grid, cudaStream_t st) {
+    auto kern = force_sym_kernel<TI, DETECT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymSmem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kFastThreads, kSymSmem, st>>>(a);
+    return cudaGetLastError();
+}
+
+const char* sym_kernel_name(int ti, bool detect) {
+    static char buf[64];
+    snprintf(buf, sizeof buf, "force_sym_kernel<%d,%s>", ti, detect ? "true" : "false");
+    return buf;
+}
+
+void free_sym(SymPlan& p) {
+    for (auto& pan : p.panels) cudaFree(pan.d_items);
+    p.panels.clear();
+    cudaFree(p.Pi);
+    cudaFree(p.Pj);
+    p.Pi = p.Pj = nullptr;
+    p.valid = false;
+}
+
+// Build the item lists (one per panel of I-blocks) and allocate the partial planes.
+cudaError_t plan_sym(SymPlan& p, long long n, int sm_count) {
+    free_sym(p);
+    const char* env_ti = getenv("ORBITAL_B200_SYM_TI");
+    int ti = 4;
+    if (n < 64 * 1024) ti = 2;
+    if (n < 16 * 1024) ti = 1;
+    if (env_ti) {
+        const int v = atoi(env_ti);
+        if (v == 1 || v == 2 || v == 4 || v == 6) ti = v;
+    }
+    p.ti = ti;
+    p.n = n;
+    p.B = (long long)kFastThreads * ti;
+    p.nb_I = (int)((n + p.B - 1) / p.B);
+    p.n_tiles = (int)((n + kTile - 1) / kTile);
+    int occ = 0;
+    switch (ti) {
+        case 1: occ = sym_occupancy<1, false>(); break;
+        case 2: occ = sym_occupancy<2, false>(); break;
+        case 4: occ = sym_occupancy<4, false>(); break;
+        default: occ = sym_occupancy<6, false>(); break;
+    }
+    if (occ <= 0) occ = 2;
+    p.ctas_per_sm = occ;
+    const long long slots = (long long)sm_count * occ;
+    // chunking: ~16 items per resident slot over the triangle
+    long long want_chunks = (32 * slots + p.nb_I - 1) / std::max(1, p.nb_I);
+    const char* env_c = getenv("ORBITAL_B200_SYM_CHUNKS");
+    if (env_c) want_chunks = atoi(env_c);
+    want_chunks = std::max<long long>(1, std::min<long long>(std::min<long long>(want_chunks, 96), p.n_tiles));
+    p.chunk_tiles = (int)((p.n_tiles + want_chunks - 1) / want_chunks);
+    p.n_chunks = (p.n_tiles + p.chunk_tiles - 1) / p.chunk_tiles;
+    // panels: bound the P_j footprint
+    long long budget = 4LL << 30;
+    const char* env_b = getenv("ORBITAL_B200_SYM_PJ_BYTES");
+    if (env_b) budget = atoll(env_b);
+    const long long per_block = 3 * n * 8;
+    p.panel_blocks = (int)std::max<long long>(1, std::min<long long>(p.nb_I, budget / per_block));
+    cudaError_t e;
+    if ((e = cudaMalloc(&p.Pi, sizeof(double) * 3 * n * p.n_chunks)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p.Pj, sizeof(double) * 3 * n * p.panel_blocks)) != cudaSuccess) return e;
+    for (int Ia = 0; Ia < p.nb_I; Ia += p.panel_blocks) {
+        SymPanel pan;
+        pan.I_base = Ia;
+        pan.I_end = std::min(p.nb_I, Ia + p.panel_blocks);
+        std::vector<SymItem> items;
+        for (int I = pan.I_base; I < pan.I_end; ++I) {
+            const int first_tile = (int)(((long long)I * p.B) / kTile);
+            for (int c = first_tile / p.chunk_tiles; c < p.n_chunks; ++c) {
+                SymItem it;
+                it.I = I;
+                it.t0 = std::max(c * p.chunk_tiles, first_tile);
+                it.t1 = std::min((c + 1) * p.chunk_tiles, p.n_tiles);
+                it.chunk = c;
+                if (it.t1 > it.t0) items.push_back(it);
+            }
+        }
+        std::stable_sort(items.begin(), items.end(),
+                         [](const SymItem& a, const SymItem& b) { return (a.t1 - a.t0) > (b.t1 - b.t0); });
+        pan.n_items = (int)items.size();
+        if ((e = cudaMalloc(&pan.d_items, sizeof(SymItem) * items.size())) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(pan.d_items, items.data(), sizeof(SymItem) * items.size(), cudaMemcpyHostToDevice)) !=
+            cudaSuccess)
+            return e;
+        p.panels.push_back(pan);
+    }
+    p.valid = true;
+    return cudaSuccess;
+}
+
+cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const SymPlan& p, bool detect,
+                             cudaStream_t st, int* launches) {
+    SymArgs a;
+    a.pos4 = s.pos4;
+    a.radius = s.radius;
+    a.Pi = p.Pi;
+    a.Pj = p.Pj;
+    a.n = s.n;
+    a.n_tiles = p.n_tiles;
+    a.eps2 = sp.eps2;
+    a.rmax1 = sp.rmax1;
+    a.rmax2 = sp.rmax2;
+    a.rmax1_idx = sp.rmax1_idx;
+    a.ctl = s.ctl;
+    a.pairs = s.pairs;
+    bool first = true;
+    for (const SymPanel& pan : p.panels) {
+        a.items = pan.d_items;
+        a.I_base = pan.I_base;
+        cudaError_t e;
+#define ORB_SYM_CASE(T)                                                                                         \
+    case T:                                                                                                     \
+        e = detect ? launch_sym_t<T, true>(a, pan.n_items, st) : launch_sym_t<T, false>(a, pan.n_items, st);   \
+        break;
+        switch (p.ti) {
+            ORB_SYM_CASE(1)
+            ORB_SYM_CASE(2)
+            ORB_SYM_CASE(4)
+            ORB_SYM_CASE(6)
+            default: return cudaErrorInvalidValue;
+        }
+#undef ORB_SYM_CASE
+        if (e != cudaSuccess) return e;
+        const int grid = (int)((s.n + 255) / 256);
+        reduce_sym_kernel<<<grid, 256, 0, st>>>(p.Pi, p.Pj, s.acc, s.n, p.B, p.chunk_tiles, p.n_chunks, pan.I_base,
+                                                pan.I_end, sp.G, first ? 0 : 1, s.ctl);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 2;
+        first = false;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace orb

@@ -1,0 +1,43 @@
+// force_sym.h -- host interface of the pair-symmetric fast force kernel (force_sym.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "kernels.h"
+
+namespace orb {
+
+struct SymItem {
+    int I;        // I-block index
+    int t0, t1;   // tile range [t0, t1)
+    int chunk;    // which P_i plane this item writes
+};
+
+struct SymPanel {
+    int I_base = 0, I_end = 0;
+    int n_items = 0;
+    SymItem* d_items = nullptr;
+};
+
+struct SymPlan {
+    bool valid = false;
+    int ti = 4;
+    long long n = 0;
+    long long B = 0;          // bodies per I-block (128 * ti)
+    int nb_I = 0, n_tiles = 0;
+    int chunk_tiles = 0, n_chunks = 0;
+    int panel_blocks = 0;
+    int ctas_per_sm = 0;
+    double* Pi = nullptr;     // [n_chunks][3][n]
+    double* Pj = nullptr;     // [panel_blocks][3][n]
+    std::vector<SymPanel> panels;
+};
+
+cudaError_t plan_sym(SymPlan& p, long long n, int sm_count);
+void free_sym(SymPlan& p);
+cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const SymPlan& p, bool detect,
+                             cudaStream_t st, int* launches);
+const char* sym_kernel_name(int ti, bool detect);
+
+}  // namespace orb

@@ -94,6 +94,7 @@ def test_force_golden_vectors_direct(nat, golden):
 @pytest.mark.parametrize("ti", ["1", "2", "4", "6", "8", None])
 def test_force_fast_within_tolerance(nat, orc, n, ti, monkeypatch):
     from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_SYM", "0")            # the one-sided kernel (also used by sharded engines)
     if ti is None:
         monkeypatch.delenv("ORBITAL_B200_TI", raising=False)
     else:
@@ -107,9 +108,52 @@ def test_force_fast_within_tolerance(nat, orc, n, ti, monkeypatch):
     dev.close()
 
 
+@pytest.mark.parametrize("n", [2, 31, 64, 257, 1000, 4096, 20000, 33333])
+@pytest.mark.parametrize("ti", ["1", "2", "4", "6", None])
+def test_force_symmetric_kernel_within_tolerance(nat, orc, n, ti, monkeypatch):
+    """Pair-symmetric kernel (default fast path on one GPU): each pair once, applied to both bodies."""
+    from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_SYM", "1")
+    if ti is None:
+        monkeypatch.delenv("ORBITAL_B200_SYM_TI", raising=False)
+    else:
+        monkeypatch.setenv("ORBITAL_B200_SYM_TI", ti)
+    c = synthetic.random_cloud(n, seed=3000 + n)
+    dev, a = device_accel(nat, c, nat.MODE_FAST)
+    assert "force_sym_kernel" in dev.force_kernel_info()["name"]
+    rows = np.arange(n, dtype=np.int64) if n <= 4096 else np.arange(0, n, 41, dtype=np.int64)
+    ref = orc.pairwise_sample(c["x"], c["y"], c["z"], c["m"], c["eps"], G, rows)
+    err = relerr(a[rows], ref)
+    assert err.max() <= TOL_FAST, f"n={n} ti={ti}: max rel err {err.max():.3e}"
+    dev.accel()
+    assert_bits(dev.download_acc().T, a, "run-to-run determinism")
+    dev.close()
+
+
+@pytest.mark.parametrize("chunks,pj_bytes", [("1", None), ("7", None), (None, str(3 * 8 * 9000 * 5)), ("3", str(3 * 8 * 9000))])
+def test_force_symmetric_chunks_and_panels(nat, orc, chunks, pj_bytes, monkeypatch):
+    """Chunked tile ranges and multi-panel P_j processing give the same answer."""
+    from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_SYM", "1")
+    monkeypatch.setenv("ORBITAL_B200_SYM_TI", "2")
+    if chunks:
+        monkeypatch.setenv("ORBITAL_B200_SYM_CHUNKS", chunks)
+    if pj_bytes:
+        monkeypatch.setenv("ORBITAL_B200_SYM_PJ_BYTES", pj_bytes)
+    c = synthetic.plummer(9000, seed=9)
+    dev, a = device_accel(nat, c, nat.MODE_FAST)
+    rows = np.arange(0, 9000, 7, dtype=np.int64)
+    ref = orc.pairwise_sample(c["x"], c["y"], c["z"], c["m"], c["eps"], G, rows)
+    assert relerr(a[rows], ref).max() <= TOL_FAST
+    F = (c["m"][:, None] * a).sum(0)
+    assert np.linalg.norm(F) <= 1e-12 * (c["m"] * np.linalg.norm(a, axis=1)).sum()
+    dev.close()
+
+
 @pytest.mark.parametrize("slabs", ["1", "3", "7"])
 def test_force_fast_slab_decomposition_is_deterministic(nat, slabs, monkeypatch):
     from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_SYM", "0")
     monkeypatch.setenv("ORBITAL_B200_SLABS", slabs)
     c = synthetic.plummer(6000, seed=5)
     dev, a1 = device_accel(nat, c, nat.MODE_FAST)

@@ -25,14 +25,21 @@ def main():
     peak = _native.fp64_peak(0, 0.5)
     print(f"fp64 peak: best {peak['tflops_best']:.2f} mean {peak['tflops_mean']:.2f} TF, clock {peak['sm_clock_mhz']:.0f} MHz")
     stream = torch.cuda.current_stream().cuda_stream
-    configs = [(ti, s) for ti in (1, 2, 4, 6, 8) for s in (None,)] + [(4, s) for s in (1, 2, 4, 8, 13, 16, 32)] \
-        + [(2, s) for s in (1, 3, 5, 8)]
+    mode = sys.argv[3] if len(sys.argv) > 3 else "sym"
+    if mode == "sym":
+        configs = [(ti, ch) for ti in (1, 2, 4, 6) for ch in (None,)] + [(4, ch) for ch in (4, 8, 16, 32, 64, 96)] \
+            + [(6, ch) for ch in (16, 48)]
+    else:
+        configs = [(ti, s) for ti in (1, 2, 4, 6, 8) for s in (None,)] + [(8, s) for s in (1, 4, 8, 16)]
     for ti, slabs in configs:
+        os.environ["ORBITAL_B200_SYM"] = "1" if mode == "sym" else "0"
         os.environ["ORBITAL_B200_TI"] = str(ti)
-        if slabs is None:
-            os.environ.pop("ORBITAL_B200_SLABS", None)
-        else:
-            os.environ["ORBITAL_B200_SLABS"] = str(slabs)
+        os.environ["ORBITAL_B200_SYM_TI"] = str(ti)
+        for key in ("ORBITAL_B200_SLABS", "ORBITAL_B200_SYM_CHUNKS"):
+            if slabs is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = str(slabs)
         dev = _native.DeviceSystem(n, 0, _native.MODE_FAST)
         dev.set_stream(stream)
         dev.set_params(c["dt"], c["eps"], c["G"])
