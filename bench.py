@@ -243,10 +243,14 @@ def run_ours(args):
         dev.upload(*cloud.arrays())
         dev.accel()
         gather = lambda: None
+        reduce_acc = lambda: None
     else:
+        reduce_acc = lambda: None
         sh = ShardedSystem(*cloud.arrays(), cloud["dt"], cloud["eps"], cloud["G"], mode=_native.MODE_FAST, device=local)
         dev = sh.dev
         gather = sh._all_gather_positions
+        if sh._partial:
+            reduce_acc = lambda: dist.all_reduce(sh._acc)
     info = dev.force_kernel_info()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
@@ -267,6 +271,7 @@ def run_ours(args):
             force_ev.append((a, b))
         else:
             dev.accel()
+        reduce_acc()
         dev.step_kick()
 
     for _ in range(max(3, args.warmup)):
@@ -302,7 +307,7 @@ def run_ours(args):
 
     def e2e_step():
         dev.upload(*[hin[k] for k in range(8)])          # H2D of this step's inputs
-        dev.step_begin(); gather(); dev.accel(); dev.step_kick()
+        dev.step_begin(); gather(); dev.accel(); reduce_acc(); dev.step_kick()
         dev.download_state(hout)                           # D2H of the step's result (synchronises)
 
     dev.accel()
@@ -329,8 +334,10 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (force pass of the local targets)
     peak = _native.fp64_peak(local, 1.0)
-    local_interactions = float(hi - lo) * n
+    local_interactions = float(hi - lo) * n        # this rank's share of the N^2 ordered interactions
     achieved_tf = FLOP_PER_INTERACTION * local_interactions / (force_ms * 1e-3) / 1e12
+    # pair-symmetric kernel: 20 FP64 instructions per unordered pair = 10 per ordered interaction; one-sided: 16
+    fp64_per_int = 10 if "force_sym" in info["name"] else 16
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": peak["tflops_mean"], "unit": "TFLOP/s",
         "frac": achieved_tf / peak["tflops_mean"], "traffic": None,
@@ -342,8 +349,8 @@ def run_ours(args):
                        "MEASURED_PEAKS.json has no FP64 figure",
         "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,
         "algorithmic_hbm_bytes_per_launch": 56 * n,
-        "fp64_instr_per_interaction": 16,
-        "fp64_pipe_util_est": achieved_tf / FLOP_PER_INTERACTION * 16 * 2 / peak["tflops_mean"],
+        "fp64_instr_per_interaction": fp64_per_int,
+        "fp64_pipe_util_est": achieved_tf / FLOP_PER_INTERACTION * fp64_per_int * 2 / peak["tflops_mean"],
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

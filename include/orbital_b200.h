@@ -128,6 +128,11 @@ int orb_step_finish(orb_engine* e);
 /* The second half of orb_step_finish on its own: half-kick (engine.py:81-82) + history append,
  * so a caller can bracket the force pass (orb_accel) with its own CUDA events. */
 int orb_step_kick(orb_engine* e);
+/* *flag != 0: on this (sharded, fast-mode) engine orb_accel leaves a PARTIAL acceleration of all n bodies
+ * (the pair-symmetric kernel evaluates a cyclic share of the pair blocks per rank); the caller must
+ * all-reduce (sum) the 3 x n buffer at orb_acc_ptr across ranks before orb_step_kick. orb_step_finish is
+ * not available then. */
+int orb_acc_needs_allreduce(orb_engine* e, int* flag);
 int orb_synchronize(orb_engine* e);
 
 /* ---- device-resident views (for torch.distributed / CUDA-event timing) -- */

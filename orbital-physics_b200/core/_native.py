@@ -63,6 +63,7 @@ SIGNATURES = {
     "orb_step_begin": (C.c_int, [_vp]),
     "orb_step_finish": (C.c_int, [_vp]),
     "orb_step_kick": (C.c_int, [_vp]),
+    "orb_acc_needs_allreduce": (C.c_int, [_vp, _intp]),
     "orb_synchronize": (C.c_int, [_vp]),
     "orb_pos4_ptr": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
     "orb_vel_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
@@ -285,6 +286,11 @@ class DeviceSystem:
 
     def step_kick(self):
         check(lib().orb_step_kick(self._h))
+
+    def acc_needs_allreduce(self) -> bool:
+        f = C.c_int(0)
+        check(lib().orb_acc_needs_allreduce(self._h, C.byref(f)))
+        return bool(f.value)
 
     def synchronize(self):
         check(lib().orb_synchronize(self._h))

@@ -6,10 +6,16 @@ contiguous target slab [lo, hi).  Per step:
 
     orb_step_begin   half-kick + drift of the local slab           (rank-local)
     all_gather       the packed {x,y,z,m} slabs, in place           (NCCL, 32*N bytes total)
-    orb_step_finish  force on local targets vs all sources + kick  (rank-local)
+    orb_accel        force pass                                     (rank-local)
+    [all_reduce      3 x N accelerations, fast mode only]           (NCCL, 24*N bytes)
+    orb_step_kick    half-kick of the local slab                    (rank-local)
 
-Each target's source order is unchanged by the partition, so the result is
-bit-identical to the single-GPU run.  The reference has no distributed path; the
+Faithful mode: every rank evaluates its own targets against all sources; each
+target's source order is unchanged by the partition, so the result is
+bit-identical to the single-GPU run.  Fast mode: the pair-symmetric kernel
+evaluates every unordered pair once, so each rank takes a cyclic share of the
+pair blocks and produces a partial acceleration of all N bodies, summed by one
+all-reduce.  The reference has no distributed path; the
 per-step semantics are the reference's core/engine.py:65-97.
 """
 from __future__ import annotations
@@ -53,8 +59,10 @@ class ShardedSystem:
         self.dev.upload(x, y, z, vx, vy, vz, m, radius, vel_is_f32)
         self._pos4 = self._view("pos4", (self.n, 4))
         self._vel = self._view("vel", (3, self.n))
+        self._acc = self._view("acc", (3, self.n))
+        self._partial = bool(self.dev.acc_needs_allreduce()) and self.world > 1
         self._bind_stream()
-        self.dev.accel()                      # engine.py:41 -- local targets vs all sources
+        self._force()                         # engine.py:41
         self.steps_done = 0
 
     # -- backend seams (overridden by the CPU test double) ------------------
@@ -62,7 +70,7 @@ class ShardedSystem:
         return _native.DeviceSystem(self.n, self.device, mode, self.lo, self.hi)
 
     def _view(self, which, shape):
-        ptr = self.dev.pos4_ptr() if which == "pos4" else self.dev.vel_ptr()
+        ptr = {"pos4": self.dev.pos4_ptr, "vel": self.dev.vel_ptr, "acc": self.dev.acc_ptr}[which]()
         return self.torch.as_tensor(_CudaView(ptr, shape), device=f"cuda:{self.device}")
 
     def _bind_stream(self):
@@ -77,11 +85,17 @@ class ShardedSystem:
         per = (self.hi - self.lo) * 4
         self.dist.all_gather_into_tensor(flat, flat[self.lo * 4: self.lo * 4 + per], group=self.group)
 
+    def _force(self):
+        self.dev.accel()
+        if self._partial:
+            self.dist.all_reduce(self._acc, group=self.group)
+
     def step(self, nsteps: int = 1):
         for _ in range(int(nsteps)):
             self.dev.step_begin()
             self._all_gather_positions()
-            self.dev.step_finish()
+            self._force()
+            self.dev.step_kick()
         self.steps_done += int(nsteps)
 
     def synchronize(self):

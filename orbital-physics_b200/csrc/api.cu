@@ -91,13 +91,28 @@ bool use_tiny(const orb_engine* e) {
     return e->mode == ORB_MODE_FAITHFUL && !e->sharded && e->s.n <= kTinyMax;
 }
 
-bool sym_applicable(const orb_engine* e) {
-    return e->mode == ORB_MODE_FAST && e->use_sym && !e->sharded;
+// world / rank of a sharded engine with equal slabs (0 when the slabs are not equal)
+int shard_world(const orb_engine* e) {
+    const long long per = e->s.tgt_hi - e->s.tgt_lo;
+    if (per <= 0 || e->s.n % per || e->s.tgt_lo % per) return 0;
+    return (int)(e->s.n / per);
 }
+
+bool sym_applicable(const orb_engine* e) {
+    return e->mode == ORB_MODE_FAST && e->use_sym && (!e->sharded || shard_world(e) > 0);
+}
+
+// pair-symmetric force on a sharded engine: every rank evaluates a cyclic share of the I-blocks and
+// ends up with a PARTIAL acceleration of all n bodies; the caller all-reduces (sum) acc across ranks.
+bool acc_is_partial(const orb_engine* e) { return e->sharded && sym_applicable(e); }
 
 int ensure_plan(orb_engine* e) {
     if (sym_applicable(e)) {
-        if (!e->sym.valid) CU(plan_sym(e->sym, e->s.n, e->sm_count));
+        if (!e->sym.valid) {
+            const int world = e->sharded ? shard_world(e) : 1;
+            const int rank = e->sharded ? (int)(e->s.tgt_lo / (e->s.tgt_hi - e->s.tgt_lo)) : 0;
+            CU(plan_sym(e->sym, e->s.n, e->sm_count, rank, world));
+        }
         return ORB_OK;
     }
     if (e->mode == ORB_MODE_FAST && !e->plan_valid) {
@@ -527,8 +542,17 @@ int orb_step_begin(orb_engine* e) {
     return ORB_OK;
 }
 
+int orb_acc_needs_allreduce(orb_engine* e, int* flag) {
+    LOCK(e);
+    if (flag) *flag = acc_is_partial(e) ? 1 : 0;
+    return ORB_OK;
+}
+
 int orb_step_finish(orb_engine* e) {
     LOCK(e);
+    if (acc_is_partial(e))
+        return fail(ORB_ERR_INVALID, "this sharded engine produces partial accelerations: use orb_accel, all-reduce "
+                                     "orb_acc_ptr across ranks, then orb_step_kick");
     int launches = 0;
     int rc = enqueue_force(e, false, &launches);
     if (rc) return rc;

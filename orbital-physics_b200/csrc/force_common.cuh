@@ -8,7 +8,10 @@ namespace orb {
 constexpr int kFastThreads = 128;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kTile = 256;     // source bodies per TMA tile (8 KiB)
-constexpr int kStages = 4;
+#ifndef ORB_STAGES
+#define ORB_STAGES 4
+#endif
+constexpr int kStages = ORB_STAGES;
 
 // m_j * (r^2)^(-3/2) to ~1 ulp from the 20-bit MUFU seed:
 //   y0 = rsqrt(r2)(1+d), e = 1 - r2*y0^2,  (r2)^(-3/2) = y0^3 (1-e)^(-3/2)

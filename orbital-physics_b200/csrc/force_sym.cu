@@ -13,8 +13,9 @@
 // 4-stage bulk-TMA ring as the one-sided kernel.
 //   * tiles that overlap the I-block ("diagonal") are processed one-sided with the self-pair masked;
 //   * tiles after it are processed symmetrically with a warp-level systolic rotation: each lane
-//     holds one tile body j and its accumulator; after every TI pairs the 7 doubles of j rotate to
-//     the neighbouring lane (14 SHFL), so after 32 steps every lane's TI bodies have met all 32
+//     meets one tile body j per step (read from the shared-memory tile) and carries j's accumulator;
+//     after every TI pairs the accumulator rotates to the neighbouring lane (6 SHFL) and the lane moves
+//     on to the next body, so after 32 steps every lane's TI bodies have met all 32
 //     bodies of the round and every j accumulator is back in its home lane.  The four warps'
 //     j-accumulators are summed in fixed order through shared memory and written to the partial
 //     plane P_j[I-block][j].
@@ -39,7 +40,6 @@ struct SymArgs {
     double* Pj;                // [panel_blocks][3][n]
     long long n;
     int n_tiles;
-    int I_base;                // first I-block of the current panel
     double eps2;
     double rmax1, rmax2;
     long long rmax1_idx;
@@ -63,10 +63,27 @@ __device__ __forceinline__ double rot1(double v, int src_lane) {
     return __shfl_sync(0xffffffffu, v, src_lane);
 }
 
-constexpr int kSymSmem = kStages * kTile * 32 + 128 + kFastWarps * 3 * kTile * 8;
+#ifndef SYM_UNROLL
+#define SYM_UNROLL 4
+#endif
+#ifndef SYM_MINB_HI
+#define SYM_MINB_HI 2   // resident CTAs/SM requested for TI >= 5
+#endif
+#ifndef SYM_SMEMROT
+#define SYM_SMEMROT 1     // 1: rotate the accumulators through shared memory (2 STS + 2 LDS) instead of 6 SHFL
+#endif
+#ifndef SYM_SPLITB
+#define SYM_SPLITB 0      // 1: two j-accumulator chains (even/odd k), merged before the rotation
+#endif
+#define ORB_STR2(x) #x
+#define ORB_STR(x) ORB_STR2(x)
+
+constexpr int kSymSlabBytes = kFastWarps * 3 * kTile * 8;
+constexpr int kSymXchgBytes = kFastWarps * 2 * 32 * 24;      // per warp: 2 buffers x 32 lanes x {xy: 16 B, z: 8 B}
+constexpr int kSymSmem = kStages * kTile * 32 + 128 + kSymSlabBytes + kSymXchgBytes;
 
 template <int TI, bool DETECT>
-__global__ void __launch_bounds__(kFastThreads, (TI >= 6 ? 2 : 3))
+__global__ void __launch_bounds__(kFastThreads, (TI >= 5 ? SYM_MINB_HI : 3))
 force_sym_kernel(const SymArgs g) {
     if (g.ctl->halted) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -74,6 +91,7 @@ force_sym_kernel(const SymArgs g) {
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTile * 32);
     uint64_t* empty = full + kStages;
     double* slab = reinterpret_cast<double*>(smem_raw + kStages * kTile * 32 + 128);   // [warp][3][kTile]
+    unsigned char* xchg_raw = smem_raw + kStages * kTile * 32 + 128 + kSymSlabBytes;
 
     const SymItem it = g.items[blockIdx.x];
     const int tid = threadIdx.x;
@@ -149,15 +167,30 @@ force_sym_kernel(const SymArgs g) {
             const int rounds = (cnt + 31) >> 5;
             for (int r = 0; r < rounds; ++r) {
                 const int slot = (r << 5) + lane;
-                const bool valid = slot < cnt;
-                const int src = valid ? slot : cnt - 1;       // padded lanes: a real position with zero mass
-                const double2 pa = tile[2 * src];
-                const double2 pb = tile[2 * src + 1];
-                double jx = pa.x, jy = pa.y, jz = pb.x;
-                double jm = valid ? pb.y : 0.0;
+                const int r32 = r << 5;
+                // body seen at step st sits in tile slot r32 + ((lane + st) & 31); padded slots (>= cnt)
+                // read a real position with zero mass
+                auto fetch = [&](int st, double& px, double& py, double& pz, double& pm) {
+                    const int sl = r32 + ((lane + st) & 31);
+                    const bool ok = sl < cnt;
+                    const int src = ok ? sl : cnt - 1;
+                    const double2 pa = tile[2 * src];
+                    const double2 pb = tile[2 * src + 1];
+                    px = pa.x; py = pa.y; pz = pb.x;
+                    pm = ok ? pb.y : 0.0;
+                };
+                double jx, jy, jz, jm;
+                fetch(0, jx, jy, jz, jm);
                 double bx = 0.0, by = 0.0, bz = 0.0;
-#pragma unroll 2
+#if SYM_SPLITB
+                double cx = 0.0, cy = 0.0, cz = 0.0;
+#endif
+_Pragma(ORB_STR(unroll SYM_UNROLL))
                 for (int st = 0; st < 32; ++st) {
+                    // next step's body comes straight from the shared-memory tile (2 LDS.128, in flight while
+                    // this step computes); only the three accumulators have to travel by shuffle
+                    double nx, ny, nz, nm;
+                    fetch(st + 1, nx, ny, nz, nm);
 #pragma unroll
                     for (int k = 0; k < TI; ++k) {
                         const double dx = jx - xi[k];
@@ -172,13 +205,35 @@ force_sym_kernel(const SymArgs g) {
                         ax[k] = fma(si, dx, ax[k]);
                         ay[k] = fma(si, dy, ay[k]);
                         az[k] = fma(si, dz, az[k]);
-                        bx = fma(-sj, dx, bx);
-                        by = fma(-sj, dy, by);
-                        bz = fma(-sj, dz, bz);
+#if SYM_SPLITB
+                        if (k & 1) {
+                            cx = fma(-sj, dx, cx); cy = fma(-sj, dy, cy); cz = fma(-sj, dz, cz);
+                        } else
+#endif
+                        {
+                            bx = fma(-sj, dx, bx);
+                            by = fma(-sj, dy, by);
+                            bz = fma(-sj, dz, bz);
+                        }
                     }
-                    jx = rot1(jx, next_lane); jy = rot1(jy, next_lane); jz = rot1(jz, next_lane);
-                    jm = rot1(jm, next_lane);
+                    jx = nx; jy = ny; jz = nz; jm = nm;
+#if SYM_SPLITB
+                    bx += cx; by += cy; bz += cz;
+                    cx = cy = cz = 0.0;
+#endif
+#if SYM_SMEMROT
+                    {
+                        double2* exy = reinterpret_cast<double2*>(xchg_raw + (size_t)warp * 2 * 32 * 24) + (st & 1) * 32;
+                        double* ez = reinterpret_cast<double*>(xchg_raw + (size_t)warp * 2 * 32 * 24 + 2 * 32 * 16) + (st & 1) * 32;
+                        exy[lane] = make_double2(bx, by);
+                        ez[lane] = bz;
+                        __syncwarp();
+                        const double2 t2 = exy[next_lane];
+                        bx = t2.x; by = t2.y; bz = ez[next_lane];
+                    }
+#else
                     bx = rot1(bx, next_lane); by = rot1(by, next_lane); bz = rot1(bz, next_lane);
+#endif
                 }
                 // 32 rotations: every accumulator is back in its home lane
                 double* mine = slab + (size_t)warp * 3 * kTile;
@@ -200,7 +255,7 @@ force_sym_kernel(const SymArgs g) {
         if (tile_index >= diag_end) {
             __syncthreads();
             // fixed-order sum of the four warps' contributions to the tile bodies -> P_j[I][j]
-            double* out = g.Pj + (long long)(it.I - g.I_base) * 3 * g.n + j0;
+            double* out = g.Pj + (long long)it.slot * 3 * g.n + j0;
             for (int e = tid; e < 3 * kTile; e += kFastThreads) {
                 const int c = e / kTile;
                 const int slot = e - c * kTile;
@@ -231,10 +286,11 @@ force_sym_kernel(const SymArgs g) {
     }
 }
 
-// a[x] (+)= G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{I-blocks of this panel before x} P_j[I][x] )
+// a[x] (+)= G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{owned I-blocks of this panel before x} P_j[slot][x] )
+// I-blocks are owned cyclically: I = rank + world * k; the panel holds k in [ka, kb).
 __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restrict__ Pi, const double* __restrict__ Pj,
                                                          double* acc, long long n, long long B, int chunk_tiles,
-                                                         int n_chunks, int I_base, int I_end, double G,
+                                                         int n_chunks, int rank, int world, int ka, int kb, double G,
                                                          int accumulate, const Ctl* ctl) {
     if (ctl->halted) return;
     const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -242,17 +298,23 @@ __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restric
     const long long X = x / B;
     const long long T = x / kTile;
     double s[3] = {0.0, 0.0, 0.0};
-    if (X >= I_base && X < I_end) {
-        const int c_first = (int)(((X * B) / kTile) / chunk_tiles);
-        for (int c = c_first; c < n_chunks; ++c) {
+    if (X % world == rank) {
+        const long long kx = (X - rank) / world;
+        if (kx >= ka && kx < kb) {
+            const int c_first = (int)(((X * B) / kTile) / chunk_tiles);
+            for (int c = c_first; c < n_chunks; ++c) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) s[k] += Pi[((long long)c * 3 + k) * n + x];
+                for (int k = 0; k < 3; ++k) s[k] += Pi[((long long)c * 3 + k) * n + x];
+            }
         }
     }
-    const long long nI = min((T * kTile) / B, (long long)I_end);
-    for (long long I = I_base; I < nI; ++I) {
+    // owned I-blocks that treated x's tile symmetrically: I < nI  <=>  k < ceil((nI - rank) / world)
+    const long long nI = (T * kTile) / B;
+    long long kend = nI > rank ? (nI - rank + world - 1) / world : 0;
+    if (kend > kb) kend = kb;
+    for (long long k = ka; k < kend; ++k) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) s[k] += Pj[((I - I_base) * 3 + k) * n + x];
+        for (int c = 0; c < 3; ++c) s[c] += Pj[((k - ka) * 3 + c) * n + x];
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -296,18 +358,22 @@ void free_sym(SymPlan& p) {
 }
 
 // Build the item lists (one per panel of I-blocks) and allocate the partial planes.
-cudaError_t plan_sym(SymPlan& p, long long n, int sm_count) {
+cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world) {
     free_sym(p);
     const char* env_ti = getenv("ORBITAL_B200_SYM_TI");
-    int ti = 4;
-    if (n < 64 * 1024) ti = 2;
-    if (n < 16 * 1024) ti = 1;
+    // measured on B200, N=262144 (profiles/r1_sweep_sym.txt): TI=7 is the sweet spot (238 registers, 2 CTAs/SM)
+    int ti = 7;
+    if (n < 128 * 1024) ti = 4;
+    if (n < 32 * 1024) ti = 2;
+    if (n < 8 * 1024) ti = 1;
     if (env_ti) {
         const int v = atoi(env_ti);
-        if (v == 1 || v == 2 || v == 4 || v == 6) ti = v;
+        if (v == 1 || v == 2 || (v >= 4 && v <= 8)) ti = v;
     }
     p.ti = ti;
     p.n = n;
+    p.rank = rank;
+    p.world = world;
     p.B = (long long)kFastThreads * ti;
     p.nb_I = (int)((n + p.B - 1) / p.B);
     p.n_tiles = (int)((n + kTile - 1) / kTile);
@@ -316,13 +382,17 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count) {
         case 1: occ = sym_occupancy<1, false>(); break;
         case 2: occ = sym_occupancy<2, false>(); break;
         case 4: occ = sym_occupancy<4, false>(); break;
-        default: occ = sym_occupancy<6, false>(); break;
+        case 5: occ = sym_occupancy<5, false>(); break;
+        case 6: occ = sym_occupancy<6, false>(); break;
+        case 7: occ = sym_occupancy<7, false>(); break;
+        default: occ = sym_occupancy<8, false>(); break;
     }
     if (occ <= 0) occ = 2;
     p.ctas_per_sm = occ;
     const long long slots = (long long)sm_count * occ;
     // chunking: ~16 items per resident slot over the triangle
-    long long want_chunks = (32 * slots + p.nb_I - 1) / std::max(1, p.nb_I);
+    const int my_blocks = (p.nb_I - rank + world - 1) / world;      // I-blocks owned by this rank (cyclic)
+    long long want_chunks = (32 * slots + my_blocks - 1) / std::max(1, my_blocks);
     const char* env_c = getenv("ORBITAL_B200_SYM_CHUNKS");
     if (env_c) want_chunks = atoi(env_c);
     want_chunks = std::max<long long>(1, std::min<long long>(std::min<long long>(want_chunks, 96), p.n_tiles));
@@ -333,16 +403,17 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count) {
     const char* env_b = getenv("ORBITAL_B200_SYM_PJ_BYTES");
     if (env_b) budget = atoll(env_b);
     const long long per_block = 3 * n * 8;
-    p.panel_blocks = (int)std::max<long long>(1, std::min<long long>(p.nb_I, budget / per_block));
+    p.panel_blocks = (int)std::max<long long>(1, std::min<long long>(std::max(1, my_blocks), budget / per_block));
     cudaError_t e;
     if ((e = cudaMalloc(&p.Pi, sizeof(double) * 3 * n * p.n_chunks)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&p.Pj, sizeof(double) * 3 * n * p.panel_blocks)) != cudaSuccess) return e;
-    for (int Ia = 0; Ia < p.nb_I; Ia += p.panel_blocks) {
+    for (int ka = 0; ka < my_blocks; ka += p.panel_blocks) {
         SymPanel pan;
-        pan.I_base = Ia;
-        pan.I_end = std::min(p.nb_I, Ia + p.panel_blocks);
+        pan.ka = ka;
+        pan.kb = std::min(my_blocks, ka + p.panel_blocks);
         std::vector<SymItem> items;
-        for (int I = pan.I_base; I < pan.I_end; ++I) {
+        for (int k = pan.ka; k < pan.kb; ++k) {
+            const int I = rank + world * k;
             const int first_tile = (int)(((long long)I * p.B) / kTile);
             for (int c = first_tile / p.chunk_tiles; c < p.n_chunks; ++c) {
                 SymItem it;
@@ -350,12 +421,14 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count) {
                 it.t0 = std::max(c * p.chunk_tiles, first_tile);
                 it.t1 = std::min((c + 1) * p.chunk_tiles, p.n_tiles);
                 it.chunk = c;
+                it.slot = k - pan.ka;
                 if (it.t1 > it.t0) items.push_back(it);
             }
         }
         std::stable_sort(items.begin(), items.end(),
                          [](const SymItem& a, const SymItem& b) { return (a.t1 - a.t0) > (b.t1 - b.t0); });
         pan.n_items = (int)items.size();
+        if (pan.n_items == 0) continue;
         if ((e = cudaMalloc(&pan.d_items, sizeof(SymItem) * items.size())) != cudaSuccess) return e;
         if ((e = cudaMemcpy(pan.d_items, items.data(), sizeof(SymItem) * items.size(), cudaMemcpyHostToDevice)) !=
             cudaSuccess)
@@ -384,7 +457,6 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
     bool first = true;
     for (const SymPanel& pan : p.panels) {
         a.items = pan.d_items;
-        a.I_base = pan.I_base;
         cudaError_t e;
 #define ORB_SYM_CASE(T)                                                                                         \
     case T:                                                                                                     \
@@ -394,18 +466,22 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
             ORB_SYM_CASE(1)
             ORB_SYM_CASE(2)
             ORB_SYM_CASE(4)
+            ORB_SYM_CASE(5)
             ORB_SYM_CASE(6)
+            ORB_SYM_CASE(7)
+            ORB_SYM_CASE(8)
             default: return cudaErrorInvalidValue;
         }
 #undef ORB_SYM_CASE
         if (e != cudaSuccess) return e;
         const int grid = (int)((s.n + 255) / 256);
-        reduce_sym_kernel<<<grid, 256, 0, st>>>(p.Pi, p.Pj, s.acc, s.n, p.B, p.chunk_tiles, p.n_chunks, pan.I_base,
-                                                pan.I_end, sp.G, first ? 0 : 1, s.ctl);
+        reduce_sym_kernel<<<grid, 256, 0, st>>>(p.Pi, p.Pj, s.acc, s.n, p.B, p.chunk_tiles, p.n_chunks, p.rank, p.world,
+                                                pan.ka, pan.kb, sp.G, first ? 0 : 1, s.ctl);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (launches) *launches += 2;
         first = false;
     }
+    if (first) return cudaMemsetAsync(s.acc, 0, sizeof(double) * 3 * s.n, st);
     return cudaSuccess;
 }
 

@@ -12,10 +12,11 @@ struct SymItem {
     int I;        // I-block index
     int t0, t1;   // tile range [t0, t1)
     int chunk;    // which P_i plane this item writes
+    int slot;     // which P_j plane of the current panel this item writes
 };
 
 struct SymPanel {
-    int I_base = 0, I_end = 0;
+    int ka = 0, kb = 0;       // owned I-blocks I = rank + world*k, k in [ka, kb)
     int n_items = 0;
     SymItem* d_items = nullptr;
 };
@@ -24,6 +25,7 @@ struct SymPlan {
     bool valid = false;
     int ti = 4;
     long long n = 0;
+    int rank = 0, world = 1;  // cyclic ownership of I-blocks (multi-GPU); 0/1 on one GPU
     long long B = 0;          // bodies per I-block (128 * ti)
     int nb_I = 0, n_tiles = 0;
     int chunk_tiles = 0, n_chunks = 0;
@@ -34,7 +36,7 @@ struct SymPlan {
     std::vector<SymPanel> panels;
 };
 
-cudaError_t plan_sym(SymPlan& p, long long n, int sm_count);
+cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world);
 void free_sym(SymPlan& p);
 cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const SymPlan& p, bool detect,
                              cudaStream_t st, int* launches);

@@ -161,6 +161,7 @@ class FakeShardedDevice:
         self.pos4 = np.zeros((self.n, 4))
         self.vel = np.zeros((3, self.n))
         self.acc = np.zeros((3, self.n))
+        self.partial = False       # True: emulate the pair-symmetric sharding (partial acc on every rank)
 
     def close(self):
         pass
@@ -178,6 +179,10 @@ class FakeShardedDevice:
 
     def accel(self):
         rows = np.arange(self.lo, self.hi, dtype=np.int64)
+        if self.partial:
+            # partial accelerations of ALL bodies whose sum over ranks is the full field: this rank
+            # contributes the rows of its own slab and zeros elsewhere (bit-exact after the all-reduce)
+            self.acc[:] = 0.0
         p = self.pos4
         a = self.orc.pairwise_sample(np.ascontiguousarray(p[:, 0]), np.ascontiguousarray(p[:, 1]),
                                      np.ascontiguousarray(p[:, 2]), np.ascontiguousarray(p[:, 3]),
@@ -204,6 +209,12 @@ class FakeShardedDevice:
     def step_finish(self):
         self.accel()
         self._kick()
+
+    def step_kick(self):
+        self._kick()
+
+    def acc_needs_allreduce(self):
+        return self.partial
 
     def synchronize(self):
         pass
