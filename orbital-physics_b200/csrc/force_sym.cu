@@ -361,14 +361,16 @@ void free_sym(SymPlan& p) {
 cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world) {
     free_sym(p);
     const char* env_ti = getenv("ORBITAL_B200_SYM_TI");
-    // measured on B200, N=262144 (profiles/r1_sweep_sym.txt): TI=7 is the sweet spot (238 registers, 2 CTAs/SM)
-    int ti = 7;
+    // I-blocks (128*TI bodies) must be tile aligned (a multiple or a divisor of the 256-body tile), otherwise a
+    // tile straddling two I-blocks would be treated one-sided by the lower block and its other bodies would miss
+    // those pairs: TI in {1, 2, 4, 6, 8}.  Measured on B200 at N=262144: TI=8 44.7 ms, TI=6 44.8 ms, TI=4 46.6 ms.
+    int ti = 8;
     if (n < 128 * 1024) ti = 4;
     if (n < 32 * 1024) ti = 2;
     if (n < 8 * 1024) ti = 1;
     if (env_ti) {
         const int v = atoi(env_ti);
-        if (v == 1 || v == 2 || (v >= 4 && v <= 8)) ti = v;
+        if (v == 1 || v == 2 || v == 4 || v == 6 || v == 8) ti = v;
     }
     p.ti = ti;
     p.n = n;
@@ -382,28 +384,27 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
         case 1: occ = sym_occupancy<1, false>(); break;
         case 2: occ = sym_occupancy<2, false>(); break;
         case 4: occ = sym_occupancy<4, false>(); break;
-        case 5: occ = sym_occupancy<5, false>(); break;
         case 6: occ = sym_occupancy<6, false>(); break;
-        case 7: occ = sym_occupancy<7, false>(); break;
         default: occ = sym_occupancy<8, false>(); break;
     }
     if (occ <= 0) occ = 2;
     p.ctas_per_sm = occ;
     const long long slots = (long long)sm_count * occ;
-    // chunking: ~16 items per resident slot over the triangle
     const int my_blocks = (p.nb_I - rank + world - 1) / world;      // I-blocks owned by this rank (cyclic)
-    long long want_chunks = (32 * slots + my_blocks - 1) / std::max(1, my_blocks);
-    const char* env_c = getenv("ORBITAL_B200_SYM_CHUNKS");
-    if (env_c) want_chunks = atoi(env_c);
-    want_chunks = std::max<long long>(1, std::min<long long>(std::min<long long>(want_chunks, 96), p.n_tiles));
-    p.chunk_tiles = (int)((p.n_tiles + want_chunks - 1) / want_chunks);
-    p.n_chunks = (p.n_tiles + p.chunk_tiles - 1) / p.chunk_tiles;
-    // panels: bound the P_j footprint
-    long long budget = 4LL << 30;
+    // panels: bound the P_j footprint (one 3 x n plane per owned I-block of the panel)
+    long long budget = 16LL << 30;
     const char* env_b = getenv("ORBITAL_B200_SYM_PJ_BYTES");
     if (env_b) budget = atoll(env_b);
     const long long per_block = 3 * n * 8;
     p.panel_blocks = (int)std::max<long long>(1, std::min<long long>(std::max(1, my_blocks), budget / per_block));
+    // chunking: ~32 items per resident slot in every panel (an item is one I-block x one chunk of tiles;
+    // about half of the (block, chunk) grid lies in the upper triangle)
+    long long want_chunks = (64 * slots + p.panel_blocks - 1) / p.panel_blocks;
+    const char* env_c = getenv("ORBITAL_B200_SYM_CHUNKS");
+    if (env_c) want_chunks = atoi(env_c);
+    want_chunks = std::max<long long>(1, std::min<long long>(std::min<long long>(want_chunks, 128), p.n_tiles));
+    p.chunk_tiles = (int)((p.n_tiles + want_chunks - 1) / want_chunks);
+    p.n_chunks = (p.n_tiles + p.chunk_tiles - 1) / p.chunk_tiles;
     cudaError_t e;
     if ((e = cudaMalloc(&p.Pi, sizeof(double) * 3 * n * p.n_chunks)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&p.Pj, sizeof(double) * 3 * n * p.panel_blocks)) != cudaSuccess) return e;
@@ -466,9 +467,7 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
             ORB_SYM_CASE(1)
             ORB_SYM_CASE(2)
             ORB_SYM_CASE(4)
-            ORB_SYM_CASE(5)
             ORB_SYM_CASE(6)
-            ORB_SYM_CASE(7)
             ORB_SYM_CASE(8)
             default: return cudaErrorInvalidValue;
         }

@@ -109,7 +109,7 @@ def test_force_fast_within_tolerance(nat, orc, n, ti, monkeypatch):
 
 
 @pytest.mark.parametrize("n", [2, 31, 64, 257, 1000, 4096, 20000, 33333])
-@pytest.mark.parametrize("ti", ["1", "2", "4", "6", None])
+@pytest.mark.parametrize("ti", ["1", "2", "4", "6", "8", None])
 def test_force_symmetric_kernel_within_tolerance(nat, orc, n, ti, monkeypatch):
     """Pair-symmetric kernel (default fast path on one GPU): each pair once, applied to both bodies."""
     from core import synthetic
@@ -121,7 +121,9 @@ def test_force_symmetric_kernel_within_tolerance(nat, orc, n, ti, monkeypatch):
     c = synthetic.random_cloud(n, seed=3000 + n)
     dev, a = device_accel(nat, c, nat.MODE_FAST)
     assert "force_sym_kernel" in dev.force_kernel_info()["name"]
-    rows = np.arange(n, dtype=np.int64) if n <= 4096 else np.arange(0, n, 41, dtype=np.int64)
+    # every row up to 4096; beyond that a stride plus the rows around every I-block / tile boundary
+    rows = np.arange(n, dtype=np.int64) if n <= 4096 else np.unique(np.concatenate(
+        [np.arange(0, n, 41), np.arange(0, n, 128), np.arange(127, n, 128), [n - 1]])).astype(np.int64)
     ref = orc.pairwise_sample(c["x"], c["y"], c["z"], c["m"], c["eps"], G, rows)
     err = relerr(a[rows], ref)
     assert err.max() <= TOL_FAST, f"n={n} ti={ti}: max rel err {err.max():.3e}"
