@@ -103,17 +103,18 @@ def test_two_rank_gloo_matches_single_process(orc, tmp_path, kind):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("mode", ["faithful", "fast"])
-def test_two_rank_nccl_bit_identical_to_single_gpu(orc, tmp_path, mode):
+def test_multi_rank_nccl_matches_single_gpu(orc, tmp_path, mode, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from core import _native, synthetic
     n, steps = 4096, 3
     out = tmp_path / mode
     out.mkdir()
-    mp.spawn(_worker, args=(2, _free_port(), "nccl", n, steps, str(out)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), "nccl", n, steps, str(out)), nprocs=world, join=True)
     got = np.load(out / "result.npz")
     # single-GPU run of the same kernels through the split-step entry points
     c = synthetic.plummer(n, seed=11)
