@@ -17,18 +17,39 @@
 namespace orb {
 
 
-template <bool FAITHFUL>
-__global__ void __launch_bounds__(32) ens_step_kernel(const EnsArgs g) {
-    __shared__ double4 sp[32];                      // {x,y,z,m or G*m}
-    const long long sys = blockIdx.x;
-    const int lane = threadIdx.x;
-    const int i = FAITHFUL ? lane : (lane & (g.nbp - 1));
-    const int part = FAITHFUL ? 0 : lane / g.nbp;
-    const int nparts = FAITHFUL ? 1 : 32 / g.nbp;
-    const bool owner = (i < g.nb) && (part == 0);   // lane that holds / stores body i
-    const bool body = i < g.nb;
-    const long long o = sys * g.nb + i;
-    const bool f32 = g.vel_f32 != 0;
+constexpr int kEnsMaxWarps = 8;
+
+// reference rounding of the integrator with the velocity dtype fixed at compile time
+template <bool F32>
+__device__ __forceinline__ double ens_kick(double v, double h, double a) {
+    const double r = __dadd_rn(v, __dmul_rn(h, a));
+    return F32 ? (double)__double2float_rn(r) : r;
+}
+template <bool F32>
+__device__ __forceinline__ double ens_drift(double r, double v, double dt, float dt32) {
+    if (F32) return __dadd_rn(r, (double)__fmul_rn(__double2float_rn(v), dt32));
+    return __dadd_rn(r, __dmul_rn(v, dt));
+}
+
+// One warp per system; `blockDim.x / 32` systems per CTA (1 = one CTA per system).
+// NBP = bodies rounded up to a power of two (compile time: loops fully unrolled, no index arithmetic).
+template <bool FAITHFUL, int NBP, bool F32>
+__global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsArgs g) {
+    __shared__ double4 sp_all[kEnsMaxWarps][NBP];   // {x,y,z,m or G*m}
+    const int warp = threadIdx.x >> 5;
+    double4* sp = sp_all[warp];
+    const int sys = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (sys >= (int)g.nsys) return;                 // whole warp exits together
+    const int lane = threadIdx.x & 31;
+    // lanes sharing one body in fast mode: 32/NBP, but never more than there are sources
+    constexpr int NPARTS = FAITHFUL ? 1 : ((32 / NBP) < NBP ? (32 / NBP) : NBP);
+    constexpr int NSRC = NBP / NPARTS;                      // sources per lane
+    const int i = FAITHFUL ? lane : (lane & (NBP - 1));
+    const int part = FAITHFUL ? 0 : lane / NBP;
+    const int nb = g.nb;
+    const bool body = i < nb;
+    const bool owner = body && (part == 0);         // lane that stores body i
+    const int o = sys * nb + i;
 
     double x = 0, y = 0, z = 0, m = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0;
     if (body) {                                     // replicas load the same lines (L1 hit)
@@ -37,44 +58,46 @@ __global__ void __launch_bounds__(32) ens_step_kernel(const EnsArgs g) {
         ax = g.ax[o]; ay = g.ay[o]; az = g.az[o];
     }
     const double mw = FAITHFUL ? __dmul_rn(g.G, m) : m;
+    const double h = g.h, dt = g.dt, eps2 = g.eps2;
+    const float dt32 = g.dt32;
 
     for (long long s = 0; s < g.nsteps; ++s) {
-        if (body) {
-            vx = kick_faithful(vx, g.h, ax, f32);                 // engine.py:69-70
-            vy = kick_faithful(vy, g.h, ay, f32);
-            vz = kick_faithful(vz, g.h, az, f32);
-            x = drift_faithful(x, vx, g.dt, g.dt32, f32);         // engine.py:73-75
-            y = drift_faithful(y, vy, g.dt, g.dt32, f32);
-            z = drift_faithful(z, vz, g.dt, g.dt32, f32);
-            if (part == 0) sp[i] = make_double4(x, y, z, mw);
-        }
+        vx = ens_kick<F32>(vx, h, ax);                            // engine.py:69-70
+        vy = ens_kick<F32>(vy, h, ay);
+        vz = ens_kick<F32>(vz, h, az);
+        x = ens_drift<F32>(x, vx, dt, dt32);                      // engine.py:73-75
+        y = ens_drift<F32>(y, vy, dt, dt32);
+        z = ens_drift<F32>(z, vz, dt, dt32);
+        if (lane < NBP) sp[lane] = make_double4(x, y, z, body ? mw : 0.0);   // padded bodies: zero mass
         __syncwarp();
         double bx = 0.0, by = 0.0, bz = 0.0;
         if (FAITHFUL) {
             if (body) {
-#pragma unroll 4
-                for (int j = 0; j < g.nb; ++j) {
-                    if (j == i) continue;
+#pragma unroll
+                for (int j = 0; j < NBP; ++j) {
+                    if (j == i || j >= nb) continue;
                     const double4 q = sp[j];
-                    pair_faithful(__dsub_rn(q.x, x), __dsub_rn(q.y, y), __dsub_rn(q.z, z), g.eps2, q.w, bx, by, bz);
+                    pair_faithful(__dsub_rn(q.x, x), __dsub_rn(q.y, y), __dsub_rn(q.z, z), eps2, q.w, bx, by, bz);
                 }
             }
         } else {
-            if (body) {
-                for (int j = part; j < g.nb; j += nparts) {
-                    const double4 q = sp[j];
-                    const double dx = q.x - x, dy = q.y - y, dz = q.z - z;
-                    const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, g.eps2)));
-                    const double y0 = rsqrt_seed(r2);
-                    const double u = y0 * y0;
-                    const double e = fma(-r2, u, 1.0);
-                    const double w = (q.w * y0) * u;
-                    double sc = fma(w, e * fma(1.875, e, 1.5), w);
-                    sc = (j == i) ? 0.0 : sc;
-                    bx = fma(sc, dx, bx); by = fma(sc, dy, by); bz = fma(sc, dz, bz);
-                }
+#pragma unroll
+            for (int jj = 0; jj < NSRC; ++jj) {
+                if (part >= NPARTS) break;                        // tiny systems: surplus lanes contribute zero
+                const int j = jj * NPARTS + part;
+                const double4 q = sp[j];
+                const double dx = q.x - x, dy = q.y - y, dz = q.z - z;
+                const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+                const double y0 = rsqrt_seed(r2);
+                const double u = y0 * y0;
+                const double e = fma(-r2, u, 1.0);
+                const double w = (q.w * y0) * u;
+                double sc = fma(w, e * fma(1.875, e, 1.5), w);
+                sc = (j == i) ? 0.0 : sc;                         // self pair (also kills the eps = 0 NaN)
+                bx = fma(sc, dx, bx); by = fma(sc, dy, by); bz = fma(sc, dz, bz);
             }
-            for (int off = g.nbp; off < 32; off <<= 1) {          // combine the parts
+#pragma unroll
+            for (int off = NBP; off < 32; off <<= 1) {            // combine the lanes sharing a body
                 bx += __shfl_xor_sync(0xffffffffu, bx, off);
                 by += __shfl_xor_sync(0xffffffffu, by, off);
                 bz += __shfl_xor_sync(0xffffffffu, bz, off);
@@ -82,11 +105,9 @@ __global__ void __launch_bounds__(32) ens_step_kernel(const EnsArgs g) {
             bx *= g.G; by *= g.G; bz *= g.G;
         }
         ax = bx; ay = by; az = bz;
-        if (body) {
-            vx = kick_faithful(vx, g.h, ax, f32);                 // engine.py:81-82
-            vy = kick_faithful(vy, g.h, ay, f32);
-            vz = kick_faithful(vz, g.h, az, f32);
-        }
+        vx = ens_kick<F32>(vx, h, ax);                            // engine.py:81-82
+        vy = ens_kick<F32>(vy, h, ay);
+        vz = ens_kick<F32>(vz, h, az);
         __syncwarp();
     }
     if (owner) {
@@ -162,11 +183,34 @@ __global__ void __launch_bounds__(32) ens_energy_kernel(const EnsArgs g, double*
     if (i == 0) E[sys] = e;
 }
 
-cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st) {
-    if (faithful)
-        ens_step_kernel<true><<<(unsigned)a.nsys, 32, 0, st>>>(a);
+template <bool FAITHFUL, int NBP>
+static void launch_ens_step_t(const EnsArgs& a, unsigned grid, int block, cudaStream_t st) {
+    if (a.vel_f32)
+        ens_step_kernel<FAITHFUL, NBP, true><<<grid, block, 0, st>>>(a);
     else
-        ens_step_kernel<false><<<(unsigned)a.nsys, 32, 0, st>>>(a);
+        ens_step_kernel<FAITHFUL, NBP, false><<<grid, block, 0, st>>>(a);
+}
+
+cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st) {
+    int w = a.warps_per_cta;
+    if (w < 1) w = 1;
+    if (w > kEnsMaxWarps) w = kEnsMaxWarps;
+    const unsigned grid = (unsigned)((a.nsys + w - 1) / w);
+    const int block = 32 * w;
+#define ORB_ENS_CASE(P)                                                       \
+    case P:                                                                   \
+        if (faithful) launch_ens_step_t<true, P>(a, grid, block, st);         \
+        else launch_ens_step_t<false, P>(a, grid, block, st);                 \
+        break;
+    switch (a.nbp) {
+        ORB_ENS_CASE(2)
+        ORB_ENS_CASE(4)
+        ORB_ENS_CASE(8)
+        ORB_ENS_CASE(16)
+        ORB_ENS_CASE(32)
+        default: return cudaErrorInvalidValue;
+    }
+#undef ORB_ENS_CASE
     return cudaGetLastError();
 }
 

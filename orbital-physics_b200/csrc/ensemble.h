@@ -11,6 +11,7 @@ struct EnsArgs {
     double h, dt, eps2, G;
     float dt32;
     int vel_f32;
+    int warps_per_cta;     // systems per CTA (one warp each); 1 = one CTA per system
 };
 cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st);
 cudaError_t launch_ens_accel(const EnsArgs& a, bool faithful, cudaStream_t st);
