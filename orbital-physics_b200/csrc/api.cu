@@ -600,9 +600,9 @@ int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, in
     const char* nm;
     int g = 0, b = 0, sm = 0, lps = 4;
     if (use_tiny(e)) {
-        nm = "tiny_steps_kernel";
-        g = 1; b = std::max(32, (int)((e->s.n + 31) / 32) * 32);
-        sm = (int)(e->s.n * 40 + 16); lps = 1;
+        nm = e->s.n <= 64 ? "micro_steps_kernel" : "tiny_steps_kernel";
+        g = 1; b = tiny_block((int)e->s.n);
+        sm = (int)(e->s.n * 64 + 16); lps = 1;
     } else if (e->mode == ORB_MODE_FAST) {
         int rc = ensure_plan(e);
         if (rc) return rc;

@@ -47,6 +47,19 @@ __device__ __forceinline__ void pair_faithful(double dx, double dy, double dz, d
     az = __dadd_rn(az, __dmul_rn(s, dz));
 }
 
+// The same pair, but returning the three products s*d without accumulating: lets many lanes evaluate
+// terms in parallel while one lane adds them in the reference's ascending-j order.
+__device__ __forceinline__ void pair_term_faithful(double dx, double dy, double dz, double eps2, double Gm,
+                                                   double& tx, double& ty, double& tz) {
+    const double r2 = __dadd_rn(dot3_numpy(dx, dy, dz), eps2);     // :146
+    const double inv_r = __ddiv_rn(1.0, __dsqrt_rn(r2));           // :147
+    const double inv_r3 = __ddiv_rn(inv_r, r2);                    // :148
+    const double s = __dmul_rn(Gm, inv_r3);                        // :151
+    tx = __dmul_rn(s, dx);                                         // :151 (a_i = s * rij)
+    ty = __dmul_rn(s, dy);
+    tz = __dmul_rn(s, dz);
+}
+
 // core/engine.py:70,82: `obj.velocity += 0.5 * dt * acc`  (h = 0.5*dt formed on the host)
 __device__ __forceinline__ double kick_faithful(double v, double h, double a, bool f32) {
     const double r = __dadd_rn(v, __dmul_rn(h, a));

@@ -13,8 +13,8 @@
 //       pipe instructions. FP64-pipe bound; HBM traffic is 56 B/body/pass.
 //       Work is a 2-D grid of (target block x source slab) items sized to fill
 //       148 SMs in whole waves; slab partials are combined in fixed order.
-//   force_faithful_kernel<DETECT>  bit-exact: one thread per target, ascending j,
-//       the reference's rounding sequence with IEEE sqrt/div.
+//   force_faithful_kernel<TW,DETECT>  bit-exact: the reference's rounding sequence with IEEE sqrt/div
+//       (SURVEY.md A.1); lanes evaluate pair terms in parallel, one lane per target adds them in ascending j.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -312,69 +312,121 @@ cudaError_t launch_force_fast(const DeviceState& s, const StepParams& p, const F
 // ===========================================================================
 // Faithful kernel: one thread per target, ascending j, exact rounding sequence
 // ===========================================================================
-template <bool DETECT>
-__global__ void force_faithful_kernel(const double4* __restrict__ pos4, const double* __restrict__ radius,
-                                      double* acc, long long n, long long tgt_lo, long long tgt_hi, double eps2,
-                                      double G, Ctl* ctl, long long* pairs) {
+// Bit-exact force kernel.  A warp owns TW targets; for every chunk of 32 sources lane l evaluates the TW
+// terms (target t, source l) with the reference's rounding sequence and parks them in shared memory;
+// lanes t < TW then add their target's 32 terms in ascending source order.  The expensive part (IEEE
+// sqrt + two divides per pair) is spread over all lanes; only the three adds per pair stay sequential,
+// which is what bit-exactness requires (physics.py:154 accumulates in loop order).
+constexpr int kFaithWarps = 4;
+
+template <int TW, bool DETECT>
+__global__ void __launch_bounds__(32 * kFaithWarps)
+force_faithful_kernel(const double4* __restrict__ pos4, const double* __restrict__ radius, double* acc, long long n,
+                      long long tgt_lo, long long tgt_hi, double eps2, double G, Ctl* ctl, long long* pairs) {
     if (ctl->halted) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double4* sp = reinterpret_cast<double4*>(smem_raw);          // blockDim sources {x,y,z,G*m}
-    double* sr = reinterpret_cast<double*>(sp + blockDim.x);     // radii
-    const long long i = tgt_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const bool active = i < tgt_hi;
-    const long long li = active ? i : tgt_hi - 1;
-    const double4 me = pos4[li];
-    const double Ri = DETECT ? radius[li] : 0.0;
-    double ax = 0.0, ay = 0.0, az = 0.0;
-    for (long long j0 = 0; j0 < n; j0 += blockDim.x) {
-        const long long jl = j0 + threadIdx.x;
-        if (jl < n) {
-            double4 q = pos4[jl];
-            q.w = __dmul_rn(G, q.w);                             // G * mj  (physics.py:151)
-            sp[threadIdx.x] = q;
-            if (DETECT) sr[threadIdx.x] = radius[jl];
-        }
-        __syncthreads();
-        const int cnt = (int)min((long long)blockDim.x, n - j0);
-        if (active) {
-#pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const long long jg = j0 + j;
-                if (jg == i) continue;
-                const double4 q = sp[j];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // per warp: terms[3][TW][33] (+1 padding: conflict-free row reads) and its targets {x,y,z,radius}
+    typedef double TermBlock[3][TW][33];
+    TermBlock& terms = reinterpret_cast<TermBlock*>(smem_raw)[warp];
+    double4* tgt = reinterpret_cast<double4*>(smem_raw + kFaithWarps * sizeof(TermBlock)) + warp * TW;
+    const long long t_base = tgt_lo + ((long long)blockIdx.x * kFaithWarps + warp) * TW;
+    if (t_base >= tgt_hi) return;                           // warp-uniform
+    const int nt = (int)min((long long)TW, tgt_hi - t_base);
+    if (lane < TW) {
+        const long long ti = min(t_base + lane, tgt_hi - 1);
+        const double4 p = pos4[ti];
+        tgt[lane] = make_double4(p.x, p.y, p.z, DETECT ? radius[ti] : 0.0);
+    }
+    __syncwarp();
+    double bx = 0.0, by = 0.0, bz = 0.0;                    // lane t < nt: accumulator of target t (physics.py:132)
+    for (long long j0 = 0; j0 < n; j0 += 32) {
+        const long long j = j0 + lane;
+        const bool jvalid = j < n;
+        const double4 q = pos4[jvalid ? j : n - 1];
+        const double Gm = __dmul_rn(G, q.w);                // G * mj (physics.py:151)
+        const double Rj = (DETECT && jvalid) ? radius[j] : 0.0;
+#pragma unroll
+        for (int t = 0; t < TW; ++t) {
+            double tx = 0.0, ty = 0.0, tz = 0.0;            // masked pairs park +0.0: x + 0.0 == x (x is never -0.0)
+            const long long it = t_base + t;
+            if (jvalid && j != it && t < nt) {
+                const double4 me = tgt[t];
                 const double dx = __dsub_rn(q.x, me.x), dy = __dsub_rn(q.y, me.y), dz = __dsub_rn(q.z, me.z);
-                pair_faithful(dx, dy, dz, eps2, q.w, ax, ay, az);
-                if (DETECT && jg > i) {
-                    if (overlap_exact(-dx, -dy, -dz, Ri, sr[j])) record_overlap(ctl, pairs, i, jg);
+                pair_term_faithful(dx, dy, dz, eps2, Gm, tx, ty, tz);
+                if (DETECT && j > it) {
+                    if (overlap_exact(-dx, -dy, -dz, me.w, Rj)) record_overlap(ctl, pairs, it, j);
                 }
             }
+            terms[0][t][lane] = tx;
+            terms[1][t][lane] = ty;
+            terms[2][t][lane] = tz;
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane < nt) {
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) {                  // ascending j: the reference's accumulation order
+                bx = __dadd_rn(bx, terms[0][lane][l]);
+                by = __dadd_rn(by, terms[1][lane][l]);
+                bz = __dadd_rn(bz, terms[2][lane][l]);
+            }
+        }
+        __syncwarp();
     }
-    if (active) {
-        acc[i] = ax;
-        acc[i + n] = ay;
-        acc[i + 2 * n] = az;
+    if (lane < nt) {
+        const long long i = t_base + lane;
+        acc[i] = bx;
+        acc[i + n] = by;
+        acc[i + 2 * n] = bz;
     }
 }
 
+// targets per warp: few, so that many warps are in flight and the fully unrolled term loop stays small
+static int faithful_tw(long long n_tgt) {
+    const char* env = getenv("ORBITAL_B200_FAITHFUL_TW");
+    if (env) {
+        const int v = atoi(env);
+        if (v == 4 || v == 8 || v == 16 || v == 32) return v;
+    }
+    // measured on B200 (faithful force pass): n=4096: TW=4 0.25 ms, 8 0.31, 16 0.54, 32 0.98;
+    // n=16384: TW=4 1.80 ms, 8 1.55 (FP64-throughput bound), 16 2.34, 32 3.87
+    return n_tgt <= 8192 ? 4 : 8;
+}
+
 void faithful_geometry(long long n_tgt, int* grid, int* block) {
-    const int b = n_tgt <= 32768 ? 32 : 128;
-    *block = b;
-    *grid = (int)((n_tgt + b - 1) / b);
+    const int tw = faithful_tw(n_tgt);
+    *block = 32 * kFaithWarps;
+    *grid = (int)((n_tgt + (long long)tw * kFaithWarps - 1) / ((long long)tw * kFaithWarps));
+}
+
+template <int TW>
+static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool detect, int grid, cudaStream_t st) {
+    const int smem = kFaithWarps * (3 * TW * 33 * 8 + TW * 32);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(force_faithful_kernel<TW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(force_faithful_kernel<TW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    if (detect)
+        force_faithful_kernel<TW, true><<<grid, 32 * kFaithWarps, smem, st>>>(s.pos4, s.radius, s.acc, s.n, s.tgt_lo,
+                                                                            s.tgt_hi, p.eps2, p.G, s.ctl, s.pairs);
+    else
+        force_faithful_kernel<TW, false><<<grid, 32 * kFaithWarps, smem, st>>>(s.pos4, s.radius, s.acc, s.n, s.tgt_lo,
+                                                                             s.tgt_hi, p.eps2, p.G, s.ctl, s.pairs);
 }
 
 cudaError_t launch_force_faithful(const DeviceState& s, const StepParams& p, bool detect, cudaStream_t st,
                                   int* launches) {
     int grid, block;
     faithful_geometry(s.tgt_hi - s.tgt_lo, &grid, &block);
-    const size_t smem = (size_t)block * (sizeof(double4) + sizeof(double));
-    if (detect)
-        force_faithful_kernel<true><<<grid, block, smem, st>>>(s.pos4, s.radius, s.acc, s.n, s.tgt_lo, s.tgt_hi,
-                                                                p.eps2, p.G, s.ctl, s.pairs);
-    else
-        force_faithful_kernel<false><<<grid, block, smem, st>>>(s.pos4, s.radius, s.acc, s.n, s.tgt_lo, s.tgt_hi,
-                                                                 p.eps2, p.G, s.ctl, s.pairs);
+    switch (faithful_tw(s.tgt_hi - s.tgt_lo)) {
+        case 4: launch_faithful_t<4>(s, p, detect, grid, st); break;
+        case 8: launch_faithful_t<8>(s, p, detect, grid, st); break;
+        case 16: launch_faithful_t<16>(s, p, detect, grid, st); break;
+        default: launch_faithful_t<32>(s, p, detect, grid, st); break;
+    }
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -107,35 +107,43 @@ cudaError_t launch_hist_append(const DeviceState& s, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // Fused small-system kernel: ONE CTA integrates the whole system for nsteps
 // steps (engine.py:65-97 per step) with all state in registers / shared memory.
-// Thread i owns body i; sources are broadcast from shared memory in ascending j
-// (bit-exact accumulation order). Two block barriers per step.
+// Thread i owns body i for the kicks and the drift.  The force pass is spread over
+// the whole CTA: a warp takes a target, its lanes evaluate the pair terms of 32
+// sources at once (IEEE sqrt + two divides each: the long-latency part), and the
+// terms are then added in ascending source order -- the reference's accumulation
+// order, so the result is bit-exact -- via warp shuffles.  Two block barriers per
+// step; the solar-system configs run 10,000 steps in a single launch.
 // ---------------------------------------------------------------------------
 template <bool DETECT>
-__global__ void __launch_bounds__(kTinyMax) tiny_steps_kernel(double4* pos4, double* vel, double* acc,
-                                                              const double* __restrict__ radius,
-                                                              const uint8_t* __restrict__ vf32, int n,
-                                                              long long nsteps, double h, double dt, float dt32,
-                                                              double eps2, double G, double* hist,
-                                                              long long hist_cap, Ctl* ctl, long long* pairs) {
+__global__ void __launch_bounds__(512, 1) tiny_steps_kernel(double4* pos4, double* vel, double* acc,
+                                                          const double* __restrict__ radius,
+                                                          const uint8_t* __restrict__ vf32, int n, long long nsteps,
+                                                          double h, double dt, float dt32, double eps2, double G,
+                                                          double* hist, long long hist_cap, Ctl* ctl,
+                                                          long long* pairs) {
     if (ctl->halted) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double4* sp = reinterpret_cast<double4*>(smem_raw);     // {x,y,z,G*m}
-    double* sr = reinterpret_cast<double*>(sp + n);
+    double* sr = reinterpret_cast<double*>(sp + n);         // radius
+    double* sa = sr + n;                                    // 3 x n accelerations of the current force build
     const int i = threadIdx.x;
+    const int lane = i & 31;
+    const int warp = i >> 5;
+    const int nwarps = blockDim.x >> 5;
     const bool active = i < n;
-    double x = 0, y = 0, z = 0, gm = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, Ri = 0;
+    double x = 0, y = 0, z = 0, gm = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0;
     bool f32 = false;
     if (active) {
         const double4 p = pos4[i];
         x = p.x; y = p.y; z = p.z;
-        gm = __dmul_rn(G, p.w);
+        gm = __dmul_rn(G, p.w);                              // G * mj (physics.py:151)
         vx = vel[i]; vy = vel[i + n]; vz = vel[i + 2 * n];
         ax = acc[i]; ay = acc[i + n]; az = acc[i + 2 * n];
         f32 = vf32[i] != 0;
-        Ri = radius[i];
-        sr[i] = Ri;
+        sr[i] = radius[i];
     }
     const long long hist0 = ctl->hist_count;
+    long long slot = hist_cap > 0 ? hist0 % hist_cap : 0;    // ring cursor, advanced without a 64-bit modulo per step
     long long done = 0;
     for (long long s = 0; s < nsteps; ++s) {
         if (active) {
@@ -149,33 +157,55 @@ __global__ void __launch_bounds__(kTinyMax) tiny_steps_kernel(double4* pos4, dou
         }
         __syncthreads();
         int hit = 0;
-        if (active) {
-            double bx = 0.0, by = 0.0, bz = 0.0;                     // physics.py:132
+        for (int t = warp; t < n; t += nwarps) {                     // warp-uniform: one target per warp pass
+            const double4 me = sp[t];
+            const double Rt = DETECT ? sr[t] : 0.0;
+            double bx = 0.0, by = 0.0, bz = 0.0;                     // physics.py:132 (replicated in every lane)
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                double tx = 0.0, ty = 0.0, tz = 0.0;
+                if (j < n && j != t) {
+                    const double4 q = sp[j];
+                    const double dx = __dsub_rn(q.x, me.x), dy = __dsub_rn(q.y, me.y), dz = __dsub_rn(q.z, me.z);
+                    pair_term_faithful(dx, dy, dz, eps2, q.w, tx, ty, tz);
+                    if (DETECT && j > t) {
+                        if (overlap_exact(-dx, -dy, -dz, Rt, sr[j])) {
+                            record_overlap(ctl, pairs, t, j);
+                            hit = 1;
+                        }
+                    }
+                }
+                const int cnt = min(32, n - j0);
 #pragma unroll 4
-            for (int j = 0; j < n; ++j) {
-                if (j == i) continue;
-                const double4 q = sp[j];
-                const double dx = __dsub_rn(q.x, x), dy = __dsub_rn(q.y, y), dz = __dsub_rn(q.z, z);
-                pair_faithful(dx, dy, dz, eps2, q.w, bx, by, bz);
-                if (DETECT && j > i) {
-                    if (overlap_exact(-dx, -dy, -dz, Ri, sr[j])) {
-                        record_overlap(ctl, pairs, i, j);
-                        hit = 1;
+                for (int l = 0; l < cnt; ++l) {                      // ascending j: the reference's order
+                    const double px = __shfl_sync(0xffffffffu, tx, l);
+                    const double py = __shfl_sync(0xffffffffu, ty, l);
+                    const double pz = __shfl_sync(0xffffffffu, tz, l);
+                    if (j0 + l != t) {                               // uniform: the self pair is skipped, not added
+                        bx = __dadd_rn(bx, px);
+                        by = __dadd_rn(by, py);
+                        bz = __dadd_rn(bz, pz);
                     }
                 }
             }
-            ax = bx; ay = by; az = bz;
+            if (lane == 0) {
+                sa[t] = bx; sa[n + t] = by; sa[2 * n + t] = bz;
+            }
+        }
+        const int hits = DETECT ? __syncthreads_or(hit) : (__syncthreads(), 0);
+        if (active) {
+            ax = sa[i]; ay = sa[n + i]; az = sa[2 * n + i];
             vx = kick_faithful(vx, h, ax, f32);                      // engine.py:81-82
             vy = kick_faithful(vy, h, ay, f32);
             vz = kick_faithful(vz, h, az, f32);
         }
-        const int hits = DETECT ? __syncthreads_or(hit) : (__syncthreads(), 0);
         ++done;
         if (hits) break;
         if (active && hist_cap > 0) {                                // engine.py:88-92
-            double* row = hist + (((hist0 + s) % hist_cap) * n + i) * 3;
+            double* row = hist + (slot * n + i) * 3;
             row[0] = x; row[1] = y; row[2] = z;
         }
+        if (++slot >= hist_cap) slot = 0;
     }
     if (active) {
         pos4[i] = make_double4(x, y, z, pos4[i].w);
@@ -193,11 +223,184 @@ __global__ void __launch_bounds__(kTinyMax) tiny_steps_kernel(double4* pos4, dou
     }
 }
 
+// ---------------------------------------------------------------------------
+// Micro-system kernel (n <= kMicroMax, e.g. the solar-system configs): same contract as
+// tiny_steps_kernel, but every unordered pair is evaluated ONCE per step -- the reference's own
+// half-matrix loop (physics.py:136-155) -- and both of its terms are parked in a shared-memory
+// matrix T[target][source]; one lane per target then adds its row in ascending source order.
+//   pair (i<j): d = rj - ri, inv_r3 shared;   T[i][j] = (G mj inv_r3) d
+//                                            T[j][i] = -((G mi inv_r3) d)   == (G mi inv_r3)(ri - rj) bit for bit
+// (IEEE negation is exact and rounding is sign-symmetric).  The expensive IEEE sqrt + two divides are
+// paid n(n-1)/2 times instead of n(n-1), spread over all lanes of the CTA.
+// ---------------------------------------------------------------------------
+constexpr int kMicroMax = 64;
+
+template <bool DETECT>
+__global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, double* vel, double* acc,
+                                                             const double* __restrict__ radius,
+                                                             const uint8_t* __restrict__ vf32, int n,
+                                                             long long nsteps, double h, double dt, float dt32,
+                                                             double eps2, double G, double* hist, long long hist_cap,
+                                                             Ctl* ctl, long long* pairs) {
+    if (ctl->halted) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int stride = n | 1;                               // odd row stride: conflict-free column walks
+    double4* sp = reinterpret_cast<double4*>(smem_raw);     // {x,y,z,G*m}
+    double* sr = reinterpret_cast<double*>(sp + n);         // radius
+    double* T = sr + n;                                     // 3 x n x stride
+    unsigned short* plist = reinterpret_cast<unsigned short*>(T + 3 * n * stride);   // (i << 8) | j, i < j
+    const int tid = threadIdx.x;
+    const int npairs = n * (n - 1) / 2;
+    for (int p = tid; p < npairs; p += blockDim.x) {        // lexicographic pair list: p -> (i, j), i < j
+        // row i starts at offset i(2n - i - 1)/2: invert with a float sqrt, then correct by at most one
+        int i = (int)((2.0f * n - 1.0f - sqrtf((2.0f * n - 1.0f) * (2.0f * n - 1.0f) - 8.0f * p)) * 0.5f);
+        i = max(0, min(i, n - 2));
+        while (i > 0 && i * (2 * n - i - 1) / 2 > p) --i;
+        while ((i + 1) * (2 * n - i - 2) / 2 <= p) ++i;
+        const int j = p - i * (2 * n - i - 1) / 2 + i + 1;
+        plist[p] = (unsigned short)((i << 8) | j);
+    }
+    const bool active = tid < n;
+    double x = 0, y = 0, z = 0, gm = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0;
+    bool f32 = false;
+    if (active) {
+        const double4 p = pos4[tid];
+        x = p.x; y = p.y; z = p.z;
+        gm = __dmul_rn(G, p.w);                              // G * m (physics.py:151-152)
+        vx = vel[tid]; vy = vel[tid + n]; vz = vel[tid + 2 * n];
+        ax = acc[tid]; ay = acc[tid + n]; az = acc[tid + 2 * n];
+        f32 = vf32[tid] != 0;
+        sr[tid] = radius[tid];
+        T[tid * stride + tid] = 0.0;                         // diagonal of the three term planes: +0.0
+        T[n * stride + tid * stride + tid] = 0.0;
+        T[2 * n * stride + tid * stride + tid] = 0.0;
+    }
+    __syncthreads();
+    const int first_pair = tid < npairs ? plist[tid] : 0;   // most systems: at most one pair per lane
+    const long long hist0 = ctl->hist_count;
+    long long slot = hist_cap > 0 ? hist0 % hist_cap : 0;    // ring cursor, advanced without a 64-bit modulo per step
+    long long done = 0;
+    for (long long s = 0; s < nsteps; ++s) {
+        if (active) {
+            vx = kick_faithful(vx, h, ax, f32);                      // engine.py:69-70
+            vy = kick_faithful(vy, h, ay, f32);
+            vz = kick_faithful(vz, h, az, f32);
+            x = drift_faithful(x, vx, dt, dt32, f32);                // engine.py:73-75
+            y = drift_faithful(y, vy, dt, dt32, f32);
+            z = drift_faithful(z, vz, dt, dt32, f32);
+            sp[tid] = make_double4(x, y, z, gm);
+        }
+        __syncthreads();
+        int hit = 0;
+        for (int p = tid; p < npairs; p += blockDim.x) {            // physics.py:136-155, one pair per lane
+            const int code = (p == tid) ? first_pair : plist[p];
+            const int i = code >> 8, j = code & 0xff;
+            const double4 pi = sp[i], pj = sp[j];
+            const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y), dz = __dsub_rn(pj.z, pi.z);  // :145
+            const double r2 = __dadd_rn(dot3_numpy(dx, dy, dz), eps2);                                        // :146
+            const double inv_r = __ddiv_rn(1.0, __dsqrt_rn(r2));                                              // :147
+            const double inv_r3 = __ddiv_rn(inv_r, r2);                                                       // :148
+            const double si = __dmul_rn(pj.w, inv_r3);               // (G mj) inv_r3          :151
+            const double sj = __dmul_rn(pi.w, inv_r3);               // (G mi) inv_r3          :152 (sign applied below)
+            double* Ti = T + i * stride + j;
+            double* Tj = T + j * stride + i;
+            const int plane = n * stride;
+            Ti[0] = __dmul_rn(si, dx); Ti[plane] = __dmul_rn(si, dy); Ti[2 * plane] = __dmul_rn(si, dz);
+            Tj[0] = -__dmul_rn(sj, dx); Tj[plane] = -__dmul_rn(sj, dy); Tj[2 * plane] = -__dmul_rn(sj, dz);
+            if (DETECT) {
+                if (overlap_exact(-dx, -dy, -dz, sr[i], sr[j])) {    // physics.py:517-518 (ri - rj)
+                    record_overlap(ctl, pairs, i, j);
+                    hit = 1;
+                }
+            }
+        }
+        const int hits = DETECT ? __syncthreads_or(hit) : (__syncthreads(), 0);
+        if (active) {
+            const double* row = T + tid * stride;
+            const int plane = n * stride;
+            double bx = 0.0, by = 0.0, bz = 0.0;                     // physics.py:132
+            // ascending j.  The diagonal entry holds +0.0 (set once below): x + 0.0 == x bit for bit because a
+            // running sum that starts at +0.0 can never be -0.0, so the self pair is "skipped" without a branch
+            // and the shared-memory loads pipeline freely.
+#pragma unroll 8
+            for (int j = 0; j < n; ++j) {
+                bx = __dadd_rn(bx, row[j]);
+                by = __dadd_rn(by, row[plane + j]);
+                bz = __dadd_rn(bz, row[2 * plane + j]);
+            }
+            ax = bx; ay = by; az = bz;
+            vx = kick_faithful(vx, h, ax, f32);                      // engine.py:81-82
+            vy = kick_faithful(vy, h, ay, f32);
+            vz = kick_faithful(vz, h, az, f32);
+        }
+        ++done;
+        if (hits) break;
+        if (active && hist_cap > 0) {                                // engine.py:88-92
+            double* hrow = hist + (slot * n + tid) * 3;
+            hrow[0] = x; hrow[1] = y; hrow[2] = z;
+        }
+        if (++slot >= hist_cap) slot = 0;
+    }
+    if (active) {
+        pos4[tid] = make_double4(x, y, z, pos4[tid].w);
+        vel[tid] = vx; vel[tid + n] = vy; vel[tid + 2 * n] = vz;
+        acc[tid] = ax; acc[tid + n] = ay; acc[tid + 2 * n] = az;
+    }
+    if (tid == 0) {
+        ctl->steps_done += done;
+        if (ctl->overlap_count > 0) {
+            ctl->halted = 1;
+            if (hist_cap > 0) ctl->hist_count = hist0 + (done - 1);
+        } else if (hist_cap > 0) {
+            ctl->hist_count = hist0 + done;
+        }
+    }
+}
+
+static int micro_block(int n) {
+    const int npairs = n * (n - 1) / 2;
+    const int want = std::max(n, npairs);                   // one pair per lane if it fits
+    return std::max(32, std::min(256, ((want + 31) / 32) * 32));
+}
+
+static size_t micro_smem(int n) {
+    const int stride = n | 1;
+    return (size_t)n * (sizeof(double4) + sizeof(double)) + (size_t)3 * n * stride * sizeof(double) +
+           (size_t)(n * (n - 1) / 2 + 8) * sizeof(unsigned short) + 32;
+}
+
+// one thread per body for the integrator, one warp per target (up to 16 warps) for the force pass
+int tiny_block(int n) {
+    if (n <= kMicroMax) return micro_block(n);
+    const int threads_bodies = ((n + 31) / 32) * 32;
+    const int threads_force = 32 * std::min(16, n);
+    return std::max(32, std::min(512, std::max(threads_bodies, threads_force)));
+}
+
 cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long long nsteps, bool detect,
                               cudaStream_t st) {
     const int n = (int)s.n;
-    const int block = std::max(32, ((n + 31) / 32) * 32);
-    const size_t smem = (size_t)n * (sizeof(double4) + sizeof(double)) + 16;
+    const int block = tiny_block(n);
+    if (n <= kMicroMax) {
+        const size_t msmem = micro_smem(n);
+        static bool attr_set = false;
+        if (!attr_set) {
+            const int cap = (int)micro_smem(kMicroMax);
+            cudaFuncSetAttribute(micro_steps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+            cudaFuncSetAttribute(micro_steps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+            attr_set = true;
+        }
+        if (detect)
+            micro_steps_kernel<true><<<1, block, msmem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h,
+                                                              p.dt, p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl,
+                                                              s.pairs);
+        else
+            micro_steps_kernel<false><<<1, block, msmem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h,
+                                                               p.dt, p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl,
+                                                               s.pairs);
+        return cudaGetLastError();
+    }
+    const size_t smem = (size_t)n * (sizeof(double4) + 4 * sizeof(double)) + 16;
     if (detect)
         tiny_steps_kernel<true><<<1, block, smem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h, p.dt,
                                                         p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl, s.pairs);

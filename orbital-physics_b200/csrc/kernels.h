@@ -61,6 +61,7 @@ cudaError_t launch_advance(const DeviceState& s, cudaStream_t st);
 cudaError_t launch_hist_append(const DeviceState& s, cudaStream_t st);
 // single-CTA fused multi-step kernel (faithful arithmetic), n <= kTinyMax
 constexpr int kTinyMax = 512;
+int tiny_block(int n);
 cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long long nsteps, bool detect,
                               cudaStream_t st);
 cudaError_t launch_pack(double4* pos4, const double* x, const double* y, const double* z, const double* m,
