@@ -338,9 +338,13 @@ def run_ours(args):
     achieved_tf = FLOP_PER_INTERACTION * local_interactions / (force_ms * 1e-3) / 1e12
     # pair-symmetric kernel: 20 FP64 instructions per unordered pair = 10 per ordered interaction; one-sided: 16
     fp64_per_int = 10 if "force_sym" in info["name"] else 16
+    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this exact
+    # workload (profiles/r1_force_sym_ti8_ncu.txt: dram__bytes_read 23.45 MB + dram__bytes_write 987.88 MB --
+    # the partial planes P_j); null for any other size / kernel
+    traffic = 1011329024.0 if (n == 262144 and world == 1 and info["name"] == "force_sym_kernel<8,false>") else None
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": peak["tflops_mean"], "unit": "TFLOP/s",
-        "frac": achieved_tf / peak["tflops_mean"], "traffic": None,
+        "frac": achieved_tf / peak["tflops_mean"], "traffic": traffic,
         "kernel": info["name"], "grid": info["grid"], "block": info["block"],
         "kernel_ms": force_ms, "interactions_per_launch": local_interactions,
         "flop_per_interaction": FLOP_PER_INTERACTION,
