@@ -325,3 +325,25 @@ def test_run_simulation_prints_like_reference(golden, backend, capsys):
     assert [l.split(":")[0] for l in out] == ["step 0", "step 10", "step 20"]
     assert eng.step_idx == 25
     assert_bits(state_of(eng)[0], _replay(golden, "solar9_f64", 25))
+
+
+@pytest.mark.parametrize("name", ["solar9_f32", "solar9_f64", "mixed12"])
+def test_resume_from_jsonl_frame_is_bit_identical(golden, backend, tmp_path, name):
+    """loader for the reference's write-only JSONL cache; resumed run == uninterrupted run."""
+    from core.engine import SimulationEngine, load_frames
+    g = golden(name)
+    fp = str(tmp_path / "run.jsonl")
+    full = build_engine(g, cache=True, cache_fp=fp, cache_every_n=5)
+    full.run(23)                                             # frames after steps 0, 5, 10, 15, 20
+    frames = load_frames(fp)
+    assert len(frames) == 5 and frames[2]["time_elapsed"] == 10 * full.dt
+    res = SimulationEngine.resume(fp, index=2, dt=float(g["dt"]), softening=float(g["eps"]),
+                                  restitution=float(g["restitution"]), cache=False, max_hist=None)
+    assert res.step_idx == 11 and res.time_elapsed == 11 * res.dt
+    assert [o.name for o in res.objects] == [o.name for o in full.objects]
+    assert [o.velocity.dtype for o in res.objects] == [o.velocity.dtype for o in full.objects]
+    res.run(12)                                              # steps 11..22 -> same point as `full`
+    assert res.step_idx == full.step_idx
+    pf, vf, af = state_of(full)
+    pr, vr, ar = state_of(res)
+    assert_bits(pr, pf); assert_bits(vr, vf); assert_bits(ar, af)
