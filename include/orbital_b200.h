@@ -82,6 +82,12 @@ int orb_destroy(orb_engine* e);
 /* SimulationEngine(dt=, softening=) + STANDARD.G (core/engine.py:31-32, core/constants.py:49-58). */
 int orb_set_params(orb_engine* e, double dt, double eps, double G);
 int orb_set_mode(orb_engine* e, int mode);
+/* Contact handling (core/engine.py:85 -> core/physics.py:510-535,391-422). restitution: collide_spheres'
+ * coefficient. resolve_on_device != 0: overlapping pairs are resolved on the device with the reference's
+ * sequential in-place semantics (lexicographic pair order, re-tested against current positions, float32
+ * velocity rounding), orb_step never halts and *n_overlaps reports the touching pairs resolved.
+ * resolve_on_device == 0 (default): orb_step halts and the caller resolves (see orb_step). */
+int orb_set_contacts(orb_engine* e, double restitution, int resolve_on_device);
 /* Device ring of the last `capacity` position snapshots (engine.history, core/engine.py:34,88-92).
  * 0 disables recording. Resets the ring. */
 int orb_set_history(orb_engine* e, int64_t capacity);

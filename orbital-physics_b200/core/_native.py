@@ -51,6 +51,7 @@ SIGNATURES = {
     "orb_destroy": (C.c_int, [_vp]),
     "orb_set_params": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
     "orb_set_mode": (C.c_int, [_vp, C.c_int]),
+    "orb_set_contacts": (C.c_int, [_vp, C.c_double, C.c_int]),
     "orb_set_history": (C.c_int, [_vp, C.c_int64]),
     "orb_set_stream": (C.c_int, [_vp, _vp]),
     "orb_upload": (C.c_int, [_vp] + [_f64] * 8 + [_vp]),
@@ -227,6 +228,9 @@ class DeviceSystem:
     def set_mode(self, mode: int):
         check(lib().orb_set_mode(self._h, int(mode)))
         self.mode = int(mode)
+
+    def set_contacts(self, restitution: float, on_device: bool):
+        check(lib().orb_set_contacts(self._h, float(restitution), int(bool(on_device))))
 
     def set_history(self, capacity: int):
         check(lib().orb_set_history(self._h, int(capacity)))

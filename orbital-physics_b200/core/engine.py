@@ -73,13 +73,16 @@ class SimulationEngine:
         history (mapping): uuid -> positions of that object at each recorded step.
 
     B200-specific keyword-only options (defaults reproduce the reference):
-        mode:   "auto" | "faithful" | "fast"  (env ORBITAL_B200_MODE)
-        device: CUDA device index             (env ORBITAL_B200_DEVICE / LOCAL_RANK)
+        mode:     "auto" | "faithful" | "fast"  (env ORBITAL_B200_MODE)
+        device:   CUDA device index             (env ORBITAL_B200_DEVICE / LOCAL_RANK)
+        contacts: "device" | "host"             (env ORBITAL_B200_CONTACTS) -- where overlapping pairs are
+                  resolved; both replay the reference's sequential sweep exactly. "device" never leaves the GPU.
     """
 
     def __init__(self, objects: ObjectCollection, dt: float = 1.0, softening: float = 0.0,
                  restitution: float = 1.0, max_hist: int = -1, cache: bool = True,
-                 cache_fp: str = "history.jsonl", cache_every_n: int = 300, *, mode=None, device=None):
+                 cache_fp: str = "history.jsonl", cache_every_n: int = 300, *, mode=None, device=None,
+                 contacts=None):
         self._lock = threading.RLock()
         self.objects = objects
         self.dt = float(dt)
@@ -91,6 +94,9 @@ class SimulationEngine:
             raise ValueError("cache_fp must end with .jsonl")
         self.cache_fp = cache_fp
         self._mode_req = mode
+        self._contacts = (contacts or os.environ.get("ORBITAL_B200_CONTACTS", "device")).lower()
+        if self._contacts not in ("device", "host"):
+            raise ValueError("contacts must be 'device' or 'host'")
         self._device = default_device() if device is None else int(device)
         self._G = STANDARD.G       # the reference never forwards unit_profile (engine.py:41,78)
 
@@ -146,9 +152,10 @@ class SimulationEngine:
         self._snap = g
 
     def _sync_params(self):
-        p = (float(self.dt), float(self.softening), float(self._G))
+        p = (float(self.dt), float(self.softening), float(self._G), float(self.restitution))
         if p != self._params:
-            self._dev.set_params(*p)
+            self._dev.set_params(*p[:3])
+            self._dev.set_contacts(p[3], self._contacts == "device")
             self._params = p
 
     def _hist_limit(self):
@@ -401,7 +408,10 @@ class SimulationEngine:
             self._force_version += done
             self._hist_total += done
             left -= done
-            if overlaps > 0:
+            if self._contacts == "device":
+                if done < chunk:
+                    raise RuntimeError("device stopped early although contacts are resolved on the device")
+            elif overlaps > 0:
                 self._resolve_contacts()
             elif done < chunk:
                 raise RuntimeError("device stopped early without reporting a contact")

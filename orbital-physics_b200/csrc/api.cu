@@ -42,11 +42,13 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
     } while (0)
 
-__global__ void ctl_reset_kernel(Ctl* ctl, int reset_hist) {
+__global__ void ctl_reset_kernel(Ctl* ctl, int reset_hist, int clear_u) {
     ctl->steps_done = 0;
     ctl->halted = 0;
     ctl->overlap_count = 0;
     ctl->overlap_overflow = 0;
+    ctl->contacts_total = 0;
+    if (clear_u) ctl->u_valid = 0;
     if (reset_hist) ctl->hist_count = 0;
 }
 
@@ -152,8 +154,15 @@ int enqueue_step(orb_engine* e, int* launches) {
     int rc = enqueue_force(e, e->detect, launches);
     if (rc) return rc;
     CU(launch_kick_hist(e->s, e->p, e->stream));
-    CU(launch_advance(e->s, e->stream));
-    *launches += 2;
+    ++*launches;
+    if (e->p.device_contacts && e->detect) {
+        // engine.py:85: contacts after the second half-kick -- resolved on the device, the step never halts
+        const bool ordered_u = e->mode == ORB_MODE_FAITHFUL && e->s.n <= 4096;
+        CU(launch_contacts(e->s, e->p, ordered_u, e->stream, launches));
+    } else {
+        CU(launch_advance(e->s, e->stream));
+        ++*launches;
+    }
     return ORB_OK;
 }
 
@@ -307,6 +316,7 @@ int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_
     }
     e->p.dt = 1.0; e->p.h = 0.5; e->p.dt32 = 1.0f; e->p.eps2 = 0.0; e->p.G = 6.67430e-11;
     e->p.rmax1 = e->p.rmax2 = 0.0; e->p.rmax1_idx = -1; e->p.detect = 0;
+    e->p.restitution = 1.0; e->p.device_contacts = 0;
     rc = alloc_engine(e);
     if (rc) { free_engine(e); delete e; return rc; }
     *out = e;
@@ -340,6 +350,16 @@ int orb_set_params(orb_engine* e, double dt, double eps, double G) {
     return ORB_OK;
 }
 
+int orb_set_contacts(orb_engine* e, double restitution, int resolve_on_device) {
+    LOCK(e);
+    if (e->sharded && resolve_on_device)
+        return fail(ORB_ERR_INVALID, "device-side contact resolution is not available on sharded engines");
+    e->p.restitution = restitution;
+    e->p.device_contacts = resolve_on_device ? 1 : 0;
+    drop_graphs(e);
+    return ORB_OK;
+}
+
 int orb_set_mode(orb_engine* e, int mode) {
     LOCK(e);
     if (mode != ORB_MODE_FAITHFUL && mode != ORB_MODE_FAST) return fail(ORB_ERR_INVALID, "bad mode");
@@ -361,7 +381,7 @@ int orb_set_history(orb_engine* e, int64_t capacity) {
         CU(cudaMalloc(&e->s.hist, sizeof(double) * 3 * e->s.n * capacity));
         e->s.hist_cap = capacity;
     }
-    ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 1);
+    ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 1, 0);
     CU(cudaGetLastError());
     return ORB_OK;
 }
@@ -458,7 +478,7 @@ int orb_upload_acc(orb_engine* e, const double* ax, const double* ay, const doub
 int orb_accel(orb_engine* e) {
     LOCK(e);
     if (!e->have_state) return fail(ORB_ERR_INVALID, "orb_accel before orb_upload");
-    ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 0);
+    ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 0, 1);     // a new force build: any stashed U is stale
     CU(cudaGetLastError());
     int launches = 1;
     int rc = enqueue_force(e, false, &launches);
@@ -472,7 +492,7 @@ int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_over
     if (nsteps < 0) return fail(ORB_ERR_INVALID, "negative nsteps");
     if (e->sharded) return fail(ORB_ERR_INVALID, "sharded engines step with orb_step_begin/orb_step_finish");
     cudaStream_t st = e->stream;
-    ctl_reset_kernel<<<1, 1, 0, st>>>(e->s.ctl, 0);
+    ctl_reset_kernel<<<1, 1, 0, st>>>(e->s.ctl, 0, 0);
     CU(cudaGetLastError());
     ++e->launches;
     if (nsteps > 0) {
@@ -514,7 +534,8 @@ int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_over
     CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (steps_done) *steps_done = e->h_ctl->steps_done;
-    if (n_overlaps) *n_overlaps = (int64_t)e->h_ctl->overlap_count;
+    if (n_overlaps)
+        *n_overlaps = e->p.device_contacts ? (int64_t)e->h_ctl->contacts_total : (int64_t)e->h_ctl->overlap_count;
     return ORB_OK;
 }
 
@@ -639,6 +660,10 @@ int orb_launch_count(orb_engine* e, int64_t* launches) {
 int orb_potential(orb_engine* e, double* U) {
     LOCK(e);
     if (!U) return fail(ORB_ERR_INVALID, "null U");
+    // a step with device-resolved contacts stashed U of its force build before the push-out moved bodies
+    CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->h_ctl->u_valid) { *U = e->h_ctl->u_stash; return ORB_OK; }
     const bool ordered = (e->mode == ORB_MODE_FAITHFUL) && e->s.n <= 4096;
     int launches = 0;
     CU(launch_potential(e->s, e->p, ordered, e->d_diag, e->stream, &launches));

@@ -20,7 +20,9 @@ struct Ctl {
     int halted;               // set once a step saw an overlap: later kernels no-op
     int overlap_count;        // overlapping pairs (i<j) seen in the halting step
     int overlap_overflow;     // pairs dropped because the list was full
-    int pad;
+    int u_valid;              // u_stash holds U of the last force build (stashed before contacts moved bodies)
+    double u_stash;
+    long long contacts_total; // touching pairs resolved on the device since the last orb_step began
 };
 
 constexpr int kOverlapCap = 1 << 16;   // recorded pairs per halting step

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 
+#include "contacts.cuh"
 #include "kernels.h"
 
 namespace orb {
@@ -65,6 +66,68 @@ __global__ void advance_kernel(Ctl* ctl, long long hist_cap) {
         ctl->hist_count += 1;
 }
 
+// ---- device-side contacts (physics.py:510-535 after the second half-kick, engine.py:85) -------------------
+// All four kernels are launched every step of an engine that can have contacts and return at once when the
+// force pass flagged nothing.
+
+// U belongs to the force build: stash it before the push-out moves bodies (only where `last_potential` is
+// evaluated in reference order: faithful mode, n <= 4096).
+__global__ void __launch_bounds__(256) contacts_stash_u_kernel(const double4* __restrict__ pos4, int n, double eps2,
+                                                               double G, Ctl* ctl) {
+    __shared__ double terms[256];
+    if (ctl->halted) return;
+    if (ctl->overlap_count == 0) {
+        if (threadIdx.x == 0) ctl->u_valid = 0;
+        return;
+    }
+    const double U = potential_ordered_block(pos4, n, eps2, G, terms);
+    if (threadIdx.x == 0) { ctl->u_stash = U; ctl->u_valid = 1; }
+}
+
+__global__ void __launch_bounds__(256) contacts_resolve_kernel(double4* pos4, double* vel, long long n,
+                                                               const double* __restrict__ radius,
+                                                               const uint8_t* __restrict__ vf32, double restitution,
+                                                               Ctl* ctl, long long* pairs) {
+    __shared__ unsigned long long scratch[4];
+    if (ctl->halted || ctl->overlap_count == 0) return;
+    const int hits = resolve_contacts_block(pos4, vel, n, radius, vf32, restitution, ctl, pairs, scratch);
+    if (threadIdx.x == 0) ctl->contacts_total += hits;
+}
+
+// engine.py:88-92 for a step with contacts (kick_hist_kernel skipped it): positions after the sweep
+__global__ void __launch_bounds__(256) contacts_hist_kernel(const double4* __restrict__ pos4, long long n,
+                                                            double* hist, long long hist_cap, const Ctl* ctl) {
+    if (ctl->halted || ctl->overlap_count == 0 || hist_cap <= 0) return;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 p = pos4[i];
+    double* row = hist + ((ctl->hist_count % hist_cap) * n + i) * 3;
+    row[0] = p.x; row[1] = p.y; row[2] = p.z;
+}
+
+__global__ void advance_contacts_kernel(Ctl* ctl, long long hist_cap) {
+    if (ctl->halted) return;
+    ctl->steps_done += 1;
+    if (hist_cap > 0) ctl->hist_count += 1;
+    ctl->overlap_count = 0;                      // the next force pass starts a fresh list
+}
+
+cudaError_t launch_contacts(const DeviceState& s, const StepParams& p, bool ordered_potential, cudaStream_t st,
+                            int* launches) {
+    if (ordered_potential) {
+        contacts_stash_u_kernel<<<1, 256, 0, st>>>(s.pos4, (int)s.n, p.eps2, p.G, s.ctl);
+        if (launches) ++*launches;
+    }
+    contacts_resolve_kernel<<<1, 256, 0, st>>>(s.pos4, s.vel, s.n, s.radius, s.vf32, p.restitution, s.ctl, s.pairs);
+    if (s.hist_cap > 0) {
+        contacts_hist_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, st>>>(s.pos4, s.n, s.hist, s.hist_cap, s.ctl);
+        if (launches) ++*launches;
+    }
+    advance_contacts_kernel<<<1, 1, 0, st>>>(s.ctl, s.hist_cap);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) hist_append_kernel(const double4* __restrict__ pos4, long long n,
                                                           double* hist, long long hist_cap, const Ctl* ctl) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -119,13 +182,17 @@ __global__ void __launch_bounds__(512, 1) tiny_steps_kernel(double4* pos4, doubl
                                                           const double* __restrict__ radius,
                                                           const uint8_t* __restrict__ vf32, int n, long long nsteps,
                                                           double h, double dt, float dt32, double eps2, double G,
-                                                          double* hist, long long hist_cap, Ctl* ctl,
+                                                          double* hist, long long hist_cap, double restitution, int device_contacts, int stash_u, Ctl* ctl,
                                                           long long* pairs) {
     if (ctl->halted) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double4* sp = reinterpret_cast<double4*>(smem_raw);     // {x,y,z,G*m}
     double* sr = reinterpret_cast<double*>(sp + n);         // radius
     double* sa = sr + n;                                    // 3 x n accelerations of the current force build
+    double* cterms = sa + 3 * n;                            // contact path: 512 doubles + 4 words of scratch
+    unsigned long long* cscratch = reinterpret_cast<unsigned long long*>(cterms + 512);
+    bool u_set = false;
+    if (threadIdx.x == 0) ctl->u_valid = 0;
     const int i = threadIdx.x;
     const int lane = i & 31;
     const int warp = i >> 5;
@@ -200,7 +267,32 @@ __global__ void __launch_bounds__(512, 1) tiny_steps_kernel(double4* pos4, doubl
             vz = kick_faithful(vz, h, az, f32);
         }
         ++done;
-        if (hits) break;
+        if (hits) {
+            if (!device_contacts) break;                             // the host resolves and resumes
+            // engine.py:85: contacts after the second half-kick, resolved here in the reference's order
+            if (active) {
+                pos4[i] = make_double4(x, y, z, pos4[i].w);
+                vel[i] = vx; vel[i + n] = vy; vel[i + 2 * n] = vz;
+            }
+            __threadfence_block();
+            __syncthreads();
+            if (stash_u) {                                           // U of this force build (pre push-out)
+                const double U = potential_ordered_block(pos4, n, eps2, G, cterms);
+                if (i == 0) { ctl->u_stash = U; ctl->u_valid = 1; }
+                u_set = true;
+            }
+            const int nh = resolve_contacts_block(pos4, vel, n, radius, vf32, restitution, ctl, pairs, cscratch);
+            if (active) {
+                const double4 p = pos4[i];
+                x = p.x; y = p.y; z = p.z;
+                vx = vel[i]; vy = vel[i + n]; vz = vel[i + 2 * n];
+            }
+            if (i == 0) { ctl->contacts_total += nh; ctl->overlap_count = 0; }
+            __syncthreads();
+        } else if (u_set) {
+            if (i == 0) ctl->u_valid = 0;
+            u_set = false;
+        }
         if (active && hist_cap > 0) {                                // engine.py:88-92
             double* row = hist + (slot * n + i) * 3;
             row[0] = x; row[1] = y; row[2] = z;
@@ -241,14 +333,18 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
                                                              const uint8_t* __restrict__ vf32, int n,
                                                              long long nsteps, double h, double dt, float dt32,
                                                              double eps2, double G, double* hist, long long hist_cap,
-                                                             Ctl* ctl, long long* pairs) {
+                                                             double restitution, int device_contacts, int stash_u, Ctl* ctl, long long* pairs) {
     if (ctl->halted) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int stride = n | 1;                               // odd row stride: conflict-free column walks
     double4* sp = reinterpret_cast<double4*>(smem_raw);     // {x,y,z,G*m}
     double* sr = reinterpret_cast<double*>(sp + n);         // radius
     double* T = sr + n;                                     // 3 x n x stride
-    unsigned short* plist = reinterpret_cast<unsigned short*>(T + 3 * n * stride);   // (i << 8) | j, i < j
+    double* cterms = T + 3 * n * stride;                    // contact path: 256 doubles + 4 words of scratch
+    unsigned long long* cscratch = reinterpret_cast<unsigned long long*>(cterms + 256);
+    unsigned short* plist = reinterpret_cast<unsigned short*>(cscratch + 4);   // (i << 8) | j, i < j
+    bool u_set = false;
+    if (threadIdx.x == 0) ctl->u_valid = 0;
     const int tid = threadIdx.x;
     const int npairs = n * (n - 1) / 2;
     for (int p = tid; p < npairs; p += blockDim.x) {        // lexicographic pair list: p -> (i, j), i < j
@@ -334,7 +430,32 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             vz = kick_faithful(vz, h, az, f32);
         }
         ++done;
-        if (hits) break;
+        if (hits) {
+            if (!device_contacts) break;                             // the host resolves and resumes
+            // engine.py:85: contacts after the second half-kick, resolved here in the reference's order
+            if (active) {
+                pos4[tid] = make_double4(x, y, z, pos4[tid].w);
+                vel[tid] = vx; vel[tid + n] = vy; vel[tid + 2 * n] = vz;
+            }
+            __threadfence_block();
+            __syncthreads();
+            if (stash_u) {                                           // U of this force build (pre push-out)
+                const double U = potential_ordered_block(pos4, n, eps2, G, cterms);
+                if (tid == 0) { ctl->u_stash = U; ctl->u_valid = 1; }
+                u_set = true;
+            }
+            const int nh = resolve_contacts_block(pos4, vel, n, radius, vf32, restitution, ctl, pairs, cscratch);
+            if (active) {
+                const double4 p = pos4[tid];
+                x = p.x; y = p.y; z = p.z;
+                vx = vel[tid]; vy = vel[tid + n]; vz = vel[tid + 2 * n];
+            }
+            if (tid == 0) { ctl->contacts_total += nh; ctl->overlap_count = 0; }
+            __syncthreads();
+        } else if (u_set) {
+            if (tid == 0) ctl->u_valid = 0;
+            u_set = false;
+        }
         if (active && hist_cap > 0) {                                // engine.py:88-92
             double* hrow = hist + (slot * n + tid) * 3;
             hrow[0] = x; hrow[1] = y; hrow[2] = z;
@@ -366,7 +487,7 @@ static int micro_block(int n) {
 static size_t micro_smem(int n) {
     const int stride = n | 1;
     return (size_t)n * (sizeof(double4) + sizeof(double)) + (size_t)3 * n * stride * sizeof(double) +
-           (size_t)(n * (n - 1) / 2 + 8) * sizeof(unsigned short) + 32;
+           (256 + 4) * sizeof(double) + (size_t)(n * (n - 1) / 2 + 8) * sizeof(unsigned short) + 32;
 }
 
 // one thread per body for the integrator, one warp per target (up to 16 warps) for the force pass
@@ -381,6 +502,7 @@ cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long lo
                               cudaStream_t st) {
     const int n = (int)s.n;
     const int block = tiny_block(n);
+    const int stash = 1;          // the fused kernels only run in faithful mode: `last_potential` is reference-ordered
     if (n <= kMicroMax) {
         const size_t msmem = micro_smem(n);
         static bool attr_set = false;
@@ -392,21 +514,23 @@ cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long lo
         }
         if (detect)
             micro_steps_kernel<true><<<1, block, msmem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h,
-                                                              p.dt, p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl,
-                                                              s.pairs);
+                                                              p.dt, p.dt32, p.eps2, p.G, s.hist, s.hist_cap, p.restitution,
+                                                              p.device_contacts, stash, s.ctl, s.pairs);
         else
             micro_steps_kernel<false><<<1, block, msmem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h,
-                                                               p.dt, p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl,
-                                                               s.pairs);
+                                                               p.dt, p.dt32, p.eps2, p.G, s.hist, s.hist_cap, p.restitution,
+                                                               p.device_contacts, stash, s.ctl, s.pairs);
         return cudaGetLastError();
     }
-    const size_t smem = (size_t)n * (sizeof(double4) + 4 * sizeof(double)) + 16;
+    const size_t smem = (size_t)n * (sizeof(double4) + 4 * sizeof(double)) + (512 + 4) * sizeof(double) + 16;
     if (detect)
         tiny_steps_kernel<true><<<1, block, smem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h, p.dt,
-                                                        p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl, s.pairs);
+                                                        p.dt32, p.eps2, p.G, s.hist, s.hist_cap, p.restitution, p.device_contacts, stash,
+                                                        s.ctl, s.pairs);
     else
         tiny_steps_kernel<false><<<1, block, smem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h, p.dt,
-                                                         p.dt32, p.eps2, p.G, s.hist, s.hist_cap, s.ctl, s.pairs);
+                                                         p.dt32, p.eps2, p.G, s.hist, s.hist_cap, p.restitution, p.device_contacts, stash,
+                                                        s.ctl, s.pairs);
     return cudaGetLastError();
 }
 
@@ -449,27 +573,7 @@ cudaError_t launch_unpack(const double4* pos4, double* x, double* y, double* z, 
 __global__ void __launch_bounds__(256) potential_faithful_kernel(const double4* __restrict__ pos4, int n,
                                                                  double eps2, double G, double* out) {
     __shared__ double terms[256];
-    double U = 0.0;
-    for (int i = 0; i < n - 1; ++i) {
-        const double4 pi = pos4[i];
-        const double gmi = __dmul_rn(-G, pi.w);                       // (-G * mi)
-        for (int j0 = i + 1; j0 < n; j0 += 256) {
-            const int j = j0 + threadIdx.x;
-            if (j < n) {
-                const double4 pj = pos4[j];
-                const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y), dz = __dsub_rn(pj.z, pi.z);
-                const double r2 = __dadd_rn(dot3_numpy(dx, dy, dz), eps2);
-                const double inv_r = __ddiv_rn(1.0, __dsqrt_rn(r2));
-                terms[threadIdx.x] = __dmul_rn(__dmul_rn(gmi, pj.w), inv_r);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const int cnt = min(256, n - j0);
-                for (int k = 0; k < cnt; ++k) U = __dadd_rn(U, terms[k]);
-            }
-            __syncthreads();
-        }
-    }
+    const double U = potential_ordered_block(pos4, n, eps2, G, terms);
     if (threadIdx.x == 0) *out = U;
 }
 

@@ -32,6 +32,8 @@ struct StepParams {
     double rmax1, rmax2;      // largest / second-largest radius (fast-mode overlap prefilter)
     long long rmax1_idx;
     int detect;               // any radius > 0 (or coincident check wanted)
+    double restitution;       // collide_spheres restitution (core/engine.py:85)
+    int device_contacts;      // 1: contacts are resolved on the device, the step never halts
 };
 
 // Geometry chosen for the fast force kernel.
@@ -58,6 +60,9 @@ const char* fast_kernel_name(int ti, bool detect);
 cudaError_t launch_kick_drift(const DeviceState& s, const StepParams& p, cudaStream_t st);
 cudaError_t launch_kick_hist(const DeviceState& s, const StepParams& p, cudaStream_t st);
 cudaError_t launch_advance(const DeviceState& s, cudaStream_t st);
+// device-side contact handling (physics.py:391-422,510-535): stash U, resolve in reference order, append history
+cudaError_t launch_contacts(const DeviceState& s, const StepParams& p, bool ordered_potential, cudaStream_t st,
+                            int* launches);
 cudaError_t launch_hist_append(const DeviceState& s, cudaStream_t st);
 // single-CTA fused multi-step kernel (faithful arithmetic), n <= kTinyMax
 constexpr int kTinyMax = 512;

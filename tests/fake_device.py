@@ -30,6 +30,8 @@ class FakeDeviceSystem:
         self.pairs = np.empty((0, 2), dtype=np.int64)
         self.launches = 0
         self.closed = False
+        self.restitution, self.device_contacts = 1.0, False
+        self.u_stash = None
         FakeDeviceSystem.instances += 1
 
     def close(self):
@@ -42,6 +44,9 @@ class FakeDeviceSystem:
 
     def set_mode(self, mode):
         self.mode = mode
+
+    def set_contacts(self, restitution, on_device):
+        self.restitution, self.device_contacts = float(restitution), bool(on_device)
 
     def set_history(self, capacity):
         self.hist_cap = int(capacity)
@@ -98,7 +103,22 @@ class FakeDeviceSystem:
         done = 0
         self.pairs = np.empty((0, 2), dtype=np.int64)
         detect = bool((self.st.radius > 0).any())
+        resolved = 0
         for _ in range(int(nsteps)):
+            self.u_stash = None
+            if self.device_contacts:
+                # emulate orb_set_contacts(on_device=1): the oracle's own sweep, U stashed before the push-out
+                self.st.restitution = self.restitution
+                before = self.st.hits
+                self.st.step(1, collisions=True)
+                self.acc = np.stack([self.st.ax, self.st.ay, self.st.az])
+                if self.st.hits > before:
+                    self.u_stash = self.st.U
+                    resolved += self.st.hits - before
+                done += 1
+                self.launches += 8
+                self._append()
+                continue
             self.st.step(1, collisions=False)
             self.acc = np.stack([self.st.ax, self.st.ay, self.st.az])
             done += 1
@@ -109,7 +129,7 @@ class FakeDeviceSystem:
                     self.pairs = ov[::-1].copy()          # unsorted on purpose
                     return done, len(ov)
             self._append()
-        return done, 0
+        return done, resolved
 
     def overlap_pairs(self, cap=1 << 16):
         return self.pairs[:cap].copy(), len(self.pairs)
@@ -125,6 +145,8 @@ class FakeDeviceSystem:
 
     def potential(self):
         s = self.st
+        if self.u_stash is not None:
+            return self.u_stash
         return self.orc.potential(s.x, s.y, s.z, s.m, self.eps, self.G)
 
     def energy_angmom(self):

@@ -289,6 +289,45 @@ def test_overlap_detection_matches_exact_test(nat, mode_name, n):
     dev.close()
 
 
+@pytest.mark.parametrize("n", [100, 700])
+def test_device_side_contact_resolution_matches_oracle_sweep(nat, orc, n):
+    """orb_set_contacts(on_device=1) on the fused single-CTA path (n=100) and the multi-kernel path (n=700):
+    bit-exact with the reference's sequential sweep (oracle orc_collisions), incl. history and U."""
+    from oracle.c_oracle import State
+    rng = np.random.default_rng(n)
+    box = 8e4 if n == 100 else 3e5
+    x, y, z = (rng.uniform(-box, box, n) for _ in range(3))
+    v = rng.standard_normal((3, n)) * 400
+    m = np.exp(rng.uniform(np.log(1e14), np.log(1e16), n))
+    radius = rng.uniform(2e3, 8e3, n)
+    f32 = (np.arange(n) % 2).astype(np.uint8)
+    vel = [np.where(f32 == 1, a.astype(np.float32).astype(np.float64), a) for a in v]
+    st = State(orc, x, y, z, *vel, m, radius, f32, 2.0, 10.0, G, restitution=0.8)
+    dev = nat.DeviceSystem(n, 0, nat.MODE_FAITHFUL)
+    dev.set_params(2.0, 10.0, G)
+    dev.set_contacts(0.8, True)
+    dev.set_history(16)
+    dev.upload(x, y, z, *vel, m, radius, f32)
+    dev.accel()
+    dev.history_append()
+    total = 0
+    for k in (1, 2, 5):
+        done, resolved = dev.step(k)
+        assert done == k, "the device never halts when it resolves contacts itself"
+        total += resolved
+        for _ in range(k):
+            st.step(1, collisions=True)
+        s = dev.download_state()
+        assert_bits(np.stack([s["x"], s["y"], s["z"]], 1), st.pos, f"pos after +{k}")
+        assert_bits(np.stack([s["vx"], s["vy"], s["vz"]], 1), st.vel, f"vel after +{k}")
+        assert_bits(dev.download_acc().T, st.acc, f"acc after +{k}")
+        assert_bits(dev.potential(), st.U, f"U after +{k} (stashed before the push-out)")
+    assert total == st.hits and total > 0
+    assert dev.history_count() == 9
+    assert_bits(dev.history_download(1)[0], st.pos, "history holds post-contact positions")
+    dev.close()
+
+
 def test_engine_fast_mode_collisions_close_to_reference(golden):
     """Fast-mode engine with contacts: same contact sequence, state within 1e-9 of the reference run."""
     from tests.test_engine import build_engine, state_of

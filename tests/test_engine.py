@@ -91,10 +91,12 @@ def test_mixed_velocity_dtypes(golden, backend, name):
 @pytest.mark.parametrize("name", ["coll_hit_f32_e1", "coll_hit_f64_e1", "coll_hit_f32_e05", "coll_hit_f64_e05",
                                   "coll_dense_f32", "coll_dense_mixed"])
 @pytest.mark.parametrize("use_run", [True, False])
-def test_collisions_match_reference(golden, backend, name, use_run):
-    """Device-side detection + host-side resolution == the reference's sequential in-place sweep."""
+@pytest.mark.parametrize("contacts", ["device", "host"])
+def test_collisions_match_reference(golden, backend, name, use_run, contacts):
+    """Contacts detected in the force pass and resolved on the device (default) or on the host
+    == the reference's sequential in-place sweep, bit for bit (incl. U, E, L of the contact steps)."""
     g = golden(name)
-    check_against_golden(g, build_engine(g), use_run=use_run)
+    check_against_golden(g, build_engine(g, contacts=contacts), use_run=use_run)
 
 
 def test_two_body_example(golden, backend):
