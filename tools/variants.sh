@@ -1,8 +1,8 @@
 #!/bin/bash
 # Development aid: time the symmetric kernel for several library builds / TI values on one GPU.
 cd "$(dirname "$0")/.."
-for lib in liborbital_b200.so liborbital_b200_vsr.so; do
-  for ti in 6 7 8; do
+for lib in liborbital_b200.so; do
+  for ti in 4 6 8; do
     echo "== $lib TI=$ti"
     ORBITAL_B200_LIB=$PWD/orbital-physics_b200/csrc/$lib ORBITAL_B200_SYM_TI=$ti python - <<PY
 import os, sys
