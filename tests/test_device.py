@@ -436,3 +436,30 @@ def test_fp64_peak_microbenchmark(nat):
     p = nat.fp64_peak(0, 0.3)
     print(f"\nFP64 DFMA peak: best {p['tflops_best']:.2f} TF, mean {p['tflops_mean']:.2f} TF at {p['sm_clock_mhz']:.0f} MHz")
     assert 10.0 < p["tflops_best"] < 60.0
+
+
+def test_engine_large_n_uses_device_diagnostics(nat, orc):
+    """n > 4096: auto mode selects the fast kernel; E and L come from device reductions (engine.py:104-121)."""
+    from core import synthetic
+    from core.engine import SimulationEngine
+    from core.physics import Coordinates, Object, ObjectCollection
+    c = synthetic.plummer(5000, seed=21)
+    objs = []
+    for i in range(c.n):
+        o = Object(float(c["m"][i]), 0.0, None, Coordinates(float(c["x"][i]), float(c["y"][i]), float(c["z"][i])),
+                   angular_velocity=np.zeros(3))
+        o.velocity = np.array([c["vx"][i], c["vy"][i], c["vz"][i]])
+        objs.append(o)
+    eng = SimulationEngine(ObjectCollection(objs), dt=c["dt"], softening=c["eps"], cache=False, max_hist=-1)
+    assert "force_sym_kernel" in eng.kernel_info()["name"]
+    E0 = eng.total_energy()
+    eng.run(20)
+    E1, L1 = eng.total_energy(), eng.angular_momentum()
+    pos = np.array([o.position() for o in objs]); vel = np.array([o.velocity for o in objs])
+    K = float(np.sum(0.5 * c["m"] * (vel ** 2).sum(1)))
+    U = orc.potential(pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), c["m"], c["eps"], G)
+    assert abs(E1 - (K + U)) <= 1e-12 * abs(K + U)
+    L_ref = np.cross(pos, c["m"][:, None] * vel).sum(0)
+    assert np.linalg.norm(L1 - L_ref) <= 1e-10 * np.abs(np.cross(pos, c["m"][:, None] * vel)).sum()
+    assert abs((E1 - E0) / E0) < 1e-6                       # leapfrog energy conservation over 20 steps
+    eng.close()

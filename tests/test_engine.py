@@ -349,3 +349,42 @@ def test_resume_from_jsonl_frame_is_bit_identical(golden, backend, tmp_path, nam
     pf, vf, af = state_of(full)
     pr, vr, ar = state_of(res)
     assert_bits(pr, pf); assert_bits(vr, vf); assert_bits(ar, af)
+
+
+def test_degenerate_collections(backend):
+    """Empty and single-body collections behave like the reference: no pairs, zero acceleration, U = 0."""
+    from core.engine import SimulationEngine, run_simulation
+    from core.physics import Coordinates, Object, ObjectCollection
+    empty = SimulationEngine(ObjectCollection([]), dt=10.0, cache=False)
+    empty.step(); empty.run(3)
+    assert empty.step_idx == 4 and empty.total_energy() == 0.0 and len(empty.history) == 0
+    assert empty.angular_momentum().tolist() == [0.0, 0.0, 0.0] and empty.acc == {}
+    one = Object(5.0, 1.0, np.array([1.0, 2.0, 3.0]), Coordinates(10.0, 20.0, 30.0))
+    eng = SimulationEngine(ObjectCollection([one]), dt=2.0, cache=False, max_hist=None)
+    assert eng.acc[one.uuid].tolist() == [0.0, 0.0, 0.0] and eng.last_potential == 0.0
+    eng.run(5)
+    assert one.position().tolist() == [20.0, 40.0, 60.0]              # free drift with the fp32 velocity
+    assert eng.total_energy() == 0.5 * 5.0 * float(one.velocity @ one.velocity)
+    assert len(eng.history[one.uuid]) == 6
+    run_simulation(eng, steps=3, print_every=1)
+    assert eng.step_idx == 8
+
+
+def test_massless_and_coincident_bodies(backend, orc):
+    """Test particles (m = 0) and softened coincident bodies follow the reference arithmetic."""
+    from oracle.c_oracle import State
+    from core.engine import SimulationEngine
+    from core.physics import Coordinates, Object, ObjectCollection
+    x = np.array([0.0, 1.0e9, 1.0e9, -3.0e9, 2.0e9]); y = np.array([0.0, 0.0, 0.0, 1.0e9, 5.0e8]); z = np.zeros(5)
+    v = np.array([[0, 0, 0], [0, 3e3, 0], [0, 3e3, 10.0], [1e3, 0, 0], [0, -2e3, 5.0]], dtype=np.float64)
+    m = np.array([1e27, 0.0, 0.0, 5e24, 1e20])
+    objs = [Object(float(m[i]), 0.0, v[i], Coordinates(float(x[i]), float(y[i]), float(z[i])), angular_velocity=np.zeros(3))
+            for i in range(5)]
+    for o, vi in zip(objs, v):
+        o.velocity = vi.copy()
+    eng = SimulationEngine(ObjectCollection(objs), dt=100.0, softening=1e6, cache=False, max_hist=None)
+    st = State(orc, x, y, z, v[:, 0], v[:, 1], v[:, 2], m, np.zeros(5), 0, 100.0, 1e6)
+    eng.run(50); st.step(50)
+    pos = np.array([o.position() for o in objs]); vel = np.array([o.velocity for o in objs])
+    assert np.array_equal(pos, st.pos) and np.array_equal(vel, st.vel)
+    assert np.isfinite(pos).all()
