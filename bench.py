@@ -288,7 +288,7 @@ def run_ours(args):
     t_ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else {}
-    launches = dev.launch_count() - launches0 + args.steps        # + the flush memset per step
+    launches = dev.launch_count() - launches0        # our kernels only (torch's L2-flush fill is not counted)
     ms_total = t_ev0.elapsed_time(t_ev1)
     force_ms = float(np.mean([a.elapsed_time(b) for a, b in force_ev]))
     if world > 1:
