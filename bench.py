@@ -337,11 +337,32 @@ def run_ours(args):
     local_interactions = float(hi - lo) * n        # this rank's share of the N^2 ordered interactions
     achieved_tf = FLOP_PER_INTERACTION * local_interactions / (force_ms * 1e-3) / 1e12
     # pair-symmetric kernel: 20 FP64 instructions per unordered pair = 10 per ordered interaction; one-sided: 16
-    fp64_per_int = 10 if "force_sym" in info["name"] else 16
+    # (9 when all masses are equal: the two per-pair mass multiplies are factored out of the sum)
+    uniform = info["name"].endswith(",true>")
+    fp64_per_int = (9 if uniform else 10) if "force_sym" in info["name"] else 16
+    general = None
+    if uniform and world == 1:
+        # the same workload through the general-mass variant of the kernel, for comparison
+        os.environ["ORBITAL_B200_SYM_UNI"] = "0"
+        try:
+            dev.accel(); torch.cuda.synchronize()
+            evs = []
+            for _ in range(3):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); dev.accel(); b.record(); evs.append((a, b))
+            torch.cuda.synchronize()
+            gms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+            gtf = FLOP_PER_INTERACTION * local_interactions / (gms * 1e-3) / 1e12
+            general = {"kernel": dev.force_kernel_info()["name"], "kernel_ms": gms, "achieved": gtf,
+                       "frac": gtf / peak["tflops_mean"], "fp64_instr_per_interaction": 10,
+                       "interactions_per_s": local_interactions / (gms * 1e-3)}
+        finally:
+            del os.environ["ORBITAL_B200_SYM_UNI"]
     # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this exact
     # workload (profiles/r1_force_sym_ti8_ncu.txt: dram__bytes_read 23.45 MB + dram__bytes_write 987.88 MB --
     # the partial planes P_j); null for any other size / kernel
-    traffic = 1011329024.0 if (n == 262144 and world == 1 and info["name"] == "force_sym_kernel<8,false>") else None
+    traffic = 1011329024.0 if (n == 262144 and world == 1 and info["name"].startswith("force_sym_kernel<8,false")) else None
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": peak["tflops_mean"], "unit": "TFLOP/s",
         "frac": achieved_tf / peak["tflops_mean"], "traffic": traffic,
@@ -356,6 +377,8 @@ def run_ours(args):
         "fp64_instr_per_interaction": fp64_per_int,
         "fp64_pipe_util_est": achieved_tf / FLOP_PER_INTERACTION * fp64_per_int * 2 / peak["tflops_mean"],
     }
+    if general:
+        roofline["general_mass_variant"] = general
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -316,7 +316,7 @@ int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_
     }
     e->p.dt = 1.0; e->p.h = 0.5; e->p.dt32 = 1.0f; e->p.eps2 = 0.0; e->p.G = 6.67430e-11;
     e->p.rmax1 = e->p.rmax2 = 0.0; e->p.rmax1_idx = -1; e->p.detect = 0;
-    e->p.restitution = 1.0; e->p.device_contacts = 0;
+    e->p.restitution = 1.0; e->p.device_contacts = 0; e->p.uniform_mass = 0.0;
     rc = alloc_engine(e);
     if (rc) { free_engine(e); delete e; return rc; }
     *out = e;
@@ -423,6 +423,13 @@ int orb_upload(orb_engine* e, const double* x, const double* y, const double* z,
         if (r > r1) { r2 = r1; r1 = r; i1 = i; }
         else if (r > r2) { r2 = r; }
     }
+    // one common mass lets the pair-symmetric kernel drop its per-pair mass multiplies
+    double um = m[0];
+    for (long long i = 1; i < n && um != 0.0; ++i)
+        if (m[i] != um) um = 0.0;
+    if (!(um == um) || um - um != 0.0) um = 0.0;      // NaN / inf masses take the general path
+    if (um != e->p.uniform_mass) drop_graphs(e);
+    e->p.uniform_mass = um;
     const bool detect = r1 > 0.0;      // all radii zero: a contact can only be dist == 0, a no-op (physics.py:396)
     if (detect != e->detect || r1 != e->p.rmax1 || r2 != e->p.rmax2 || i1 != e->p.rmax1_idx) drop_graphs(e);
     e->detect = detect;
@@ -628,7 +635,7 @@ int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, in
         int rc = ensure_plan(e);
         if (rc) return rc;
         if (sym_applicable(e)) {
-            nm = sym_kernel_name(e->sym.ti, e->detect);
+            nm = sym_kernel_name(e->sym.ti, e->detect, sym_uniform(e->sym, e->p));
             g = 0;
             for (const auto& pan : e->sym.panels) g += pan.n_items;
             b = 128; sm = 0;

@@ -28,7 +28,20 @@ __device__ __forceinline__ double inv_r3_mass(double r2, double mj, int& y0_hi) 
     return fma(w, q, w);
 }
 
-template <int TI, bool DETECT, bool CHECKED>
+// y0^3 (1-e)^(-3/2) without the mass factor: 6 FP64 instructions
+__device__ __forceinline__ double inv_r3_plain(double r2, int& y0_hi) {
+    const double y0 = rsqrt_seed(r2);
+    y0_hi = __double2hiint(y0);
+    const double u = y0 * y0;
+    const double e = fma(-r2, u, 1.0);
+    const double w = y0 * u;
+    const double p = fma(1.875, e, 1.5);
+    const double q = e * p;
+    return fma(w, q, w);
+}
+
+// UNI: all masses are equal -- the mass factor is applied once, by the reduction kernel
+template <int TI, bool DETECT, bool CHECKED, bool UNI = false>
 __device__ __forceinline__ void tile_loop(const double2* __restrict__ tile, int cnt, long long j0, double eps2,
                                           const double (&xi)[TI], const double (&yi)[TI], const double (&zi)[TI],
                                           const long long (&idx)[TI], double (&ax)[TI], double (&ay)[TI],
@@ -44,7 +57,7 @@ __device__ __forceinline__ void tile_loop(const double2* __restrict__ tile, int 
             const double dz = b.x - zi[k];
             const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
             int hi;
-            double s = inv_r3_mass(r2, b.y, hi);
+            double s = UNI ? inv_r3_plain(r2, hi) : inv_r3_mass(r2, b.y, hi);
             if (CHECKED) {
                 const bool self = (j0 + j) == idx[k];
                 s = self ? 0.0 : s;

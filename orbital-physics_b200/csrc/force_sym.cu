@@ -47,18 +47,6 @@ struct SymArgs {
     long long* pairs;
 };
 
-// y0^3 (1-e)^(-3/2) without the mass factor: 6 FP64 instructions
-__device__ __forceinline__ double inv_r3_plain(double r2, int& y0_hi) {
-    const double y0 = rsqrt_seed(r2);
-    y0_hi = __double2hiint(y0);
-    const double u = y0 * y0;
-    const double e = fma(-r2, u, 1.0);
-    const double w = y0 * u;
-    const double p = fma(1.875, e, 1.5);
-    const double q = e * p;
-    return fma(w, q, w);
-}
-
 __device__ __forceinline__ double rot1(double v, int src_lane) {
     return __shfl_sync(0xffffffffu, v, src_lane);
 }
@@ -82,7 +70,10 @@ constexpr int kSymSlabBytes = kFastWarps * 3 * kTile * 8;
 constexpr int kSymXchgBytes = kFastWarps * 2 * 32 * 24;      // per warp: 2 buffers x 32 lanes x {xy: 16 B, z: 8 B}
 constexpr int kSymSmem = kStages * kTile * 32 + 128 + kSymSlabBytes + kSymXchgBytes;
 
-template <int TI, bool DETECT>
+// UNI: every body has the same mass and n is a whole number of I-blocks and tiles (no padded slots, no
+// shadow threads): the two per-pair mass multiplies disappear (18 FP64 instructions per pair) and the
+// reduction kernel scales by G*m.
+template <int TI, bool DETECT, bool UNI>
 __global__ void __launch_bounds__(kFastThreads, (TI >= 5 ? SYM_MINB_HI : 3))
 force_sym_kernel(const SymArgs g) {
     if (g.ctl->halted) return;
@@ -161,7 +152,7 @@ force_sym_kernel(const SymArgs g) {
 
         if (tile_index < diag_end) {
             // ---- diagonal tile: one-sided, self-pair masked (both directions are evaluated by their owners)
-            tile_loop<TI, DETECT, true>(tile, cnt, j0, g.eps2, xi, yi, zi, idx, ax, ay, az, maxhi);
+            tile_loop<TI, DETECT, true, UNI>(tile, cnt, j0, g.eps2, xi, yi, zi, idx, ax, ay, az, maxhi);
         } else {
             // ---- symmetric tile: systolic rotation, 32 bodies per round
             const int rounds = (cnt + 31) >> 5;
@@ -172,7 +163,7 @@ force_sym_kernel(const SymArgs g) {
                 // read a real position with zero mass
                 auto fetch = [&](int st, double& px, double& py, double& pz, double& pm) {
                     const int sl = r32 + ((lane + st) & 31);
-                    const bool ok = sl < cnt;
+                    const bool ok = UNI || sl < cnt;          // UNI: whole tiles only
                     const int src = ok ? sl : cnt - 1;
                     const double2 pa = tile[2 * src];
                     const double2 pb = tile[2 * src + 1];
@@ -200,8 +191,8 @@ _Pragma(ORB_STR(unroll SYM_UNROLL))
                         int hi;
                         const double s0 = inv_r3_plain(r2, hi);
                         if (DETECT) maxhi[k] = max(maxhi[k], hi);
-                        const double si = s0 * jm;            // physics.py:151  a_i += (G m_j / r^3) d
-                        const double sj = s0 * mi[k];         // physics.py:152  a_j -= (G m_i / r^3) d
+                        const double si = UNI ? s0 : s0 * jm;      // physics.py:151  a_i += (G m_j / r^3) d
+                        const double sj = UNI ? s0 : s0 * mi[k];   // physics.py:152  a_j -= (G m_i / r^3) d
                         ax[k] = fma(si, dx, ax[k]);
                         ay[k] = fma(si, dy, ay[k]);
                         az[k] = fma(si, dz, az[k]);
@@ -327,24 +318,24 @@ __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restric
 template <int TI, bool DETECT>
 static int sym_occupancy() {
     int nb = 0;
-    auto kern = force_sym_kernel<TI, DETECT>;
+    auto kern = force_sym_kernel<TI, DETECT, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymSmem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kFastThreads, kSymSmem) != cudaSuccess) nb = 0;
     return nb;
 }
 
-template <int TI, bool DETECT>
+template <int TI, bool DETECT, bool UNI>
 static cudaError_t launch_sym_t(const SymArgs& a, int grid, cudaStream_t st) {
-    auto kern = force_sym_kernel<TI, DETECT>;
+    auto kern = force_sym_kernel<TI, DETECT, UNI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymSmem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kFastThreads, kSymSmem, st>>>(a);
     return cudaGetLastError();
 }
 
-const char* sym_kernel_name(int ti, bool detect) {
+const char* sym_kernel_name(int ti, bool detect, bool uniform) {
     static char buf[64];
-    snprintf(buf, sizeof buf, "force_sym_kernel<%d,%s>", ti, detect ? "true" : "false");
+    snprintf(buf, sizeof buf, "force_sym_kernel<%d,%s,%s>", ti, detect ? "true" : "false", uniform ? "true" : "false");
     return buf;
 }
 
@@ -440,6 +431,13 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
     return cudaSuccess;
 }
 
+// The mass-free variant needs one common mass and no partial I-block or tile.
+bool sym_uniform(const SymPlan& p, const StepParams& sp) {
+    const char* v = getenv("ORBITAL_B200_SYM_UNI");      // "0": keep the per-pair mass multiplies (cross-check)
+    const bool off = v && v[0] == '0';
+    return !off && sp.uniform_mass != 0.0 && p.n % kTile == 0 && p.n % p.B == 0;
+}
+
 cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const SymPlan& p, bool detect,
                              cudaStream_t st, int* launches) {
     SymArgs a;
@@ -455,13 +453,20 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
     a.rmax1_idx = sp.rmax1_idx;
     a.ctl = s.ctl;
     a.pairs = s.pairs;
+    const bool uni = sym_uniform(p, sp);
+    const double scale = uni ? sp.G * sp.uniform_mass : sp.G;
     bool first = true;
     for (const SymPanel& pan : p.panels) {
         a.items = pan.d_items;
         cudaError_t e;
 #define ORB_SYM_CASE(T)                                                                                         \
     case T:                                                                                                     \
-        e = detect ? launch_sym_t<T, true>(a, pan.n_items, st) : launch_sym_t<T, false>(a, pan.n_items, st);   \
+        if (uni)                                                                                                \
+            e = detect ? launch_sym_t<T, true, true>(a, pan.n_items, st)                                        \
+                       : launch_sym_t<T, false, true>(a, pan.n_items, st);                                      \
+        else                                                                                                    \
+            e = detect ? launch_sym_t<T, true, false>(a, pan.n_items, st)                                       \
+                       : launch_sym_t<T, false, false>(a, pan.n_items, st);                                     \
         break;
         switch (p.ti) {
             ORB_SYM_CASE(1)
@@ -475,7 +480,7 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
         if (e != cudaSuccess) return e;
         const int grid = (int)((s.n + 255) / 256);
         reduce_sym_kernel<<<grid, 256, 0, st>>>(p.Pi, p.Pj, s.acc, s.n, p.B, p.chunk_tiles, p.n_chunks, p.rank, p.world,
-                                                pan.ka, pan.kb, sp.G, first ? 0 : 1, s.ctl);
+                                                pan.ka, pan.kb, scale, first ? 0 : 1, s.ctl);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (launches) *launches += 2;
         first = false;

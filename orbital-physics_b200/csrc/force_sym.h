@@ -40,6 +40,7 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
 void free_sym(SymPlan& p);
 cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const SymPlan& p, bool detect,
                              cudaStream_t st, int* launches);
-const char* sym_kernel_name(int ti, bool detect);
+bool sym_uniform(const SymPlan& p, const StepParams& sp);
+const char* sym_kernel_name(int ti, bool detect, bool uniform);
 
 }  // namespace orb

@@ -34,6 +34,7 @@ struct StepParams {
     int detect;               // any radius > 0 (or coincident check wanted)
     double restitution;       // collide_spheres restitution (core/engine.py:85)
     int device_contacts;      // 1: contacts are resolved on the device, the step never halts
+    double uniform_mass;      // the common mass when every body has the same (non-zero) mass, else 0
 };
 
 // Geometry chosen for the fast force kernel.

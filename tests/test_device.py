@@ -132,6 +132,42 @@ def test_force_symmetric_kernel_within_tolerance(nat, orc, n, ti, monkeypatch):
     dev.close()
 
 
+@pytest.mark.parametrize("n", [6144, 12288, 6000])
+@pytest.mark.parametrize("ti", ["1", "2", "4", "6", "8", None])
+def test_force_symmetric_uniform_mass_variant(nat, orc, n, ti, monkeypatch):
+    """Equal masses + whole I-blocks/tiles: the kernel drops the per-pair mass multiplies (G*m applied once)."""
+    from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_SYM", "1")
+    if ti is None:
+        monkeypatch.delenv("ORBITAL_B200_SYM_TI", raising=False)
+    else:
+        monkeypatch.setenv("ORBITAL_B200_SYM_TI", ti)
+    c = synthetic.plummer(n, seed=n)
+    assert np.all(c["m"] == c["m"][0])
+    dev, a = device_accel(nat, c, nat.MODE_FAST)
+    name = dev.force_kernel_info()["name"]
+    aligned = n % 256 == 0 and n % (128 * int(name.split("<")[1].split(",")[0])) == 0
+    assert name.endswith(",true>") == aligned, name
+    rows = np.arange(0, n, 3, dtype=np.int64)
+    ref = orc.pairwise_sample(c["x"], c["y"], c["z"], c["m"], c["eps"], G, rows)
+    assert relerr(a[rows], ref).max() <= TOL_FAST
+    monkeypatch.setenv("ORBITAL_B200_SYM_UNI", "0")          # general-mass variant on the same input
+    dev.accel()
+    assert dev.force_kernel_info()["name"].endswith(",false>")
+    b = dev.download_acc().T
+    assert relerr(a, b).max() <= 1e-13
+    # one body with a different mass must switch the variant off
+    monkeypatch.delenv("ORBITAL_B200_SYM_UNI")
+    arrs = list(c.arrays())
+    m2 = arrs[6].copy(); m2[n // 2] *= 3.0; arrs[6] = m2
+    dev.upload(*arrs)
+    dev.accel()
+    assert dev.force_kernel_info()["name"].endswith(",false>")
+    ref2 = orc.pairwise_sample(c["x"], c["y"], c["z"], m2, c["eps"], G, rows)
+    assert relerr(dev.download_acc().T[rows], ref2).max() <= TOL_FAST
+    dev.close()
+
+
 @pytest.mark.parametrize("chunks,pj_bytes", [("1", None), ("7", None), (None, str(3 * 8 * 9000 * 5)), ("3", str(3 * 8 * 9000))])
 def test_force_symmetric_chunks_and_panels(nat, orc, chunks, pj_bytes, monkeypatch):
     """Chunked tile ranges and multi-panel P_j processing give the same answer."""
