@@ -359,10 +359,15 @@ def run_ours(args):
                        "interactions_per_s": local_interactions / (gms * 1e-3)}
         finally:
             del os.environ["ORBITAL_B200_SYM_UNI"]
-    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this exact
-    # workload (profiles/r1_force_sym_ti8_ncu.txt: dram__bytes_read 23.45 MB + dram__bytes_write 987.88 MB --
-    # the partial planes P_j); null for any other size / kernel
-    traffic = 1011329024.0 if (n == 262144 and world == 1 and info["name"].startswith("force_sym_kernel<8,false")) else None
+    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` captures of this exact
+    # workload (dram__bytes_read + dram__bytes_write, almost all of it the partial planes P_j):
+    #   profiles/r1_force_sym_ti8_uniform_ncu.txt  21.89 MB + 985.64 MB   (uniform-mass variant)
+    #   profiles/r1_force_sym_ti8_ncu.txt          23.45 MB + 987.88 MB   (general variant)
+    # null for any other size / kernel
+    traffic = None
+    if n == 262144 and world == 1:
+        traffic = {"force_sym_kernel<8,false,true>": 1007530752.0,
+                   "force_sym_kernel<8,false,false>": 1011329024.0}.get(info["name"])
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": peak["tflops_mean"], "unit": "TFLOP/s",
         "frac": achieved_tf / peak["tflops_mean"], "traffic": traffic,
