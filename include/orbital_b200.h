@@ -176,15 +176,38 @@ int orb_ens_set_params(orb_ensemble* s, double dt, double eps, double G);
 int orb_ens_set_stream(orb_ensemble* s, void* cuda_stream);
 int orb_ens_upload(orb_ensemble* s, const double* x, const double* y, const double* z,
                    const double* vx, const double* vy, const double* vz, const double* m);
+/* Generate the ensemble's initial condition on the device from orbital elements
+ * (replaces nsys*(nbody-1) host calls of Body.get_state, core/body.py:184-249, and
+ * solve_kepler, core/physics.py:43-71). Body 0 of every system is the central
+ * mass at rest at the origin; bodies 1.. are parent-relative with
+ * n = sqrt(G m_0 / a^3) (core/body.py:159-169) and b = a sqrt(1-e^2) (:120-124).
+ * Element arrays are [nsys][nbody-1] (radians, metres); m is [nsys][nbody].
+ * Same operation order as the reference; differs from it only where the device
+ * sin/cos differ from the host libm (<= 2 ulp) -- within tolerance, not bit-exact. */
+int orb_ens_upload_elements(orb_ensemble* s, const double* M, const double* e, const double* a,
+                            const double* inc, const double* Omega, const double* omega,
+                            const double* m);
 /* fused != 0: all nsteps inside one launch, state in registers/shared memory
  * (FP64-bound); fused == 0: one launch per step, state round-trips HBM
- * (104 B per body-step, HBM-bound). Asynchronous. */
+ * (152 B per body-step incl. the accelerations the reference keeps between
+ * steps, engine.py:41,78; HBM-bound). Asynchronous. */
 int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused);
 int orb_ens_download(orb_ensemble* s, double* x, double* y, double* z,
                      double* vx, double* vy, double* vz);
 int orb_ens_energy(orb_ensemble* s, double* E_per_system);
 int orb_ens_synchronize(orb_ensemble* s);
 int orb_ens_launch_count(orb_ensemble* s, int64_t* launches);
+
+/* ---- initial-condition pipeline ----------------------------
+ * Batched Keplerian elements -> parent-relative Cartesian state: count bodies,
+ * host arrays in (M, inc, Omega, omega in radians; a, b in metres; n = mean
+ * motion in rad/s), host arrays out (r3, v3: [3][count]; E optional: eccentric
+ * anomaly). Replaces a Python loop over Body.get_state (core/body.py:184-249)
+ * / solve_kepler(M, e, tol, max_iter) (core/physics.py:43-71). */
+int orb_kepler_states(int device, int64_t count, const double* M, const double* e, const double* a,
+                      const double* b, const double* n, const double* inc, const double* Omega,
+                      const double* omega, double tol, int max_iter,
+                      double* r3, double* v3, double* E);
 
 #ifdef __cplusplus
 }

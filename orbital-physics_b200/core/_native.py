@@ -81,11 +81,13 @@ SIGNATURES = {
     "orb_ens_set_params": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
     "orb_ens_set_stream": (C.c_int, [_vp, _vp]),
     "orb_ens_upload": (C.c_int, [_vp] + [_f64] * 7),
+    "orb_ens_upload_elements": (C.c_int, [_vp] + [_f64] * 7),
     "orb_ens_step": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "orb_ens_download": (C.c_int, [_vp] + [_vp] * 6),
     "orb_ens_energy": (C.c_int, [_vp, _f64]),
     "orb_ens_synchronize": (C.c_int, [_vp]),
     "orb_ens_launch_count": (C.c_int, [_vp, _i64p]),
+    "orb_kepler_states": (C.c_int, [C.c_int, C.c_int64] + [_f64] * 8 + [C.c_double, C.c_int, _f64, _f64, _vp]),
 }
 
 _lib = None
@@ -357,6 +359,21 @@ class DeviceSystem:
         return out[: got.value]
 
 
+def kepler_states(M, e, a, b, n, inc, Omega, omega, tol: float = 1e-12, max_iter: int = 50, device: int = 0,
+                  return_E: bool = False):
+    """Batched elements -> parent-relative (r[count,3], v[count,3]) on the device (orb_kepler_states)."""
+    arrs = [_c64(np.atleast_1d(v)).reshape(-1) for v in (M, e, a, b, n, inc, Omega, omega)]
+    count = arrs[0].shape[0]
+    if any(v.shape[0] != count for v in arrs):
+        raise ValueError("element arrays must have the same length")
+    r3, v3 = np.empty((3, count)), np.empty((3, count))
+    E = np.empty(count) if return_E else None
+    check(lib().orb_kepler_states(int(device), count, *arrs, float(tol), int(max_iter), r3.reshape(-1),
+                                  v3.reshape(-1), _ptr(E) if return_E else None))
+    out = (np.ascontiguousarray(r3.T), np.ascontiguousarray(v3.T))
+    return out + (E,) if return_E else out
+
+
 class DeviceEnsemble:
     """nsys independent systems of nbody bodies, one CTA per system (orb_ens_*)."""
 
@@ -388,6 +405,17 @@ class DeviceEnsemble:
             if a.shape != (self.nsys, self.nbody):
                 raise ValueError(f"expected shape ({self.nsys},{self.nbody}), got {a.shape}")
         check(lib().orb_ens_upload(self._h, *[a.reshape(-1) for a in arrs]))
+
+    def upload_elements(self, M, e, a, inc, Omega, omega, m):
+        """Initial condition from orbital elements, generated on the device (orb_ens_upload_elements)."""
+        els = [_c64(v) for v in (M, e, a, inc, Omega, omega)]
+        for v in els:
+            if v.shape != (self.nsys, self.nbody - 1):
+                raise ValueError(f"expected element shape ({self.nsys},{self.nbody - 1}), got {v.shape}")
+        m = _c64(m)
+        if m.shape != (self.nsys, self.nbody):
+            raise ValueError(f"expected mass shape ({self.nsys},{self.nbody}), got {m.shape}")
+        check(lib().orb_ens_upload_elements(self._h, *[v.reshape(-1) for v in els], m.reshape(-1)))
 
     def step(self, nsteps: int = 1, fused: bool = True):
         check(lib().orb_ens_step(self._h, int(nsteps), int(bool(fused))))

@@ -1,4 +1,8 @@
-"""Keplerian-element body model: generates initial conditions (host only).
+"""Keplerian-element body model: generates initial conditions.
+
+`Body.get_state` is the host path (bit-identical to the reference); `batch_states` / `System.get_states`
+evaluate many bodies in one device launch (liborbital_b200 `orb_kepler_states`, csrc/kepler.cu: same operation
+order, device sin/cos, so within ~1e-15 relative of the host path rather than bit-identical).
 
 API-compatible with the reference's core/body.py:14-317 (`Body`, `System`).
 This is the step *before* the hot path: it runs once per body at start-up and
@@ -148,8 +152,35 @@ class Body:
         return rotate(r_pf), rotate(v_pf)
 
 
+def batch_states(bodies, device: int | None = None):
+    """Parent-relative (r[n,3], v[n,3]) of many bodies in ONE device launch.
+
+    Batched counterpart of a Python loop over `Body.get_state` (reference core/body.py:184-249); bodies without
+    a parent sit at the origin, as there.  Raises core._native.NativeError without the CUDA library/device.
+    """
+    import numpy as np
+    from core import _native
+    from core.physics import default_device
+    bodies = list(bodies)
+    idx = [k for k, bd in enumerate(bodies) if bd.parent is not None]
+    r, v = np.zeros((len(bodies), 3)), np.zeros((len(bodies), 3))
+    if idx:
+        sel = [bodies[k] for k in idx]
+        cols = ([_radians(bd.M) for bd in sel], [bd.e for bd in sel], [_metres(bd.a) for bd in sel],
+                [_metres(bd.b) for bd in sel], [bd.mean_motion() for bd in sel], [_radians(bd.I) for bd in sel],
+                [_radians(bd.long_node) for bd in sel], [_radians(bd.arg_peri) for bd in sel])
+        rr, vv = _native.kepler_states(*(np.array(c, dtype=np.float64) for c in cols),
+                                       device=default_device() if device is None else device)
+        r[idx], v[idx] = rr, vv
+    return r, v
+
+
 class System:
     """An ordered set of bodies plus the unit choice their elements are expressed in."""
+
+    def get_states(self, device: int | None = None):
+        """(r[n,3], v[n,3]) of every body, evaluated on the device in one launch (see `batch_states`)."""
+        return batch_states(self.bodies, device)
 
     def __init__(self, bodies, distance_unit="meters", mass_unit="kg", angle_unit="radians", time_unit="seconds"):
         self.bodies = bodies

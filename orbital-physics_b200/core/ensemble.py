@@ -30,6 +30,29 @@ class EnsembleEngine:
     `vel_f32=True` reproduces bodies built through `Object(...)` (float32 velocity storage).
     """
 
+    @classmethod
+    def from_elements(cls, M, e, a, inc, Omega, omega, m, dt: float, softening: float = 0.0, *,
+                      G: float = 6.67430e-11, mode: str = "fast", vel_f32: bool = False, device: int | None = None):
+        """Build the ensemble from orbital elements ON THE DEVICE (orb_ens_upload_elements, csrc/kepler.cu).
+
+        Element arrays are [nsys, nbody-1] (radians / metres) for the bodies orbiting body 0, `m` is
+        [nsys, nbody].  Replaces nsys*(nbody-1) host evaluations of the reference's `Body.get_state`
+        (core/body.py:184-249) + `solve_kepler` (core/physics.py:43-71); body 0 rests at the origin.
+        """
+        M = np.asarray(M, dtype=np.float64)
+        if M.ndim != 2:
+            raise ValueError("element arrays must be [nsys, nbody-1]")
+        self = cls.__new__(cls)
+        self.nsys, self.nbody = M.shape[0], M.shape[1] + 1
+        self.dt, self.softening, self.G = float(dt), float(softening), float(G)
+        nat_mode = {"fast": _native.MODE_FAST, "faithful": _native.MODE_FAITHFUL}[mode]
+        self._dev = _native.DeviceEnsemble(self.nsys, self.nbody, default_device() if device is None else device,
+                                           nat_mode, vel_f32)
+        self._dev.set_params(self.dt, self.softening, self.G)
+        self._dev.upload_elements(M, e, a, inc, Omega, omega, m)
+        self.steps_done = 0
+        return self
+
     def __init__(self, x, y, z, vx, vy, vz, m, dt: float, softening: float = 0.0, *, G: float = 6.67430e-11,
                  mode: str = "fast", vel_f32: bool = False, device: int | None = None):
         x = np.asarray(x, dtype=np.float64)

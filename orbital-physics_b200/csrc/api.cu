@@ -837,6 +837,60 @@ int orb_ens_upload(orb_ensemble* s, const double* x, const double* y, const doub
     return ORB_OK;
 }
 
+int orb_ens_upload_elements(orb_ensemble* s, const double* M, const double* e, const double* a, const double* inc,
+                            const double* Omega, const double* omega, const double* m) {
+    LOCK(s);
+    if (!M || !e || !a || !inc || !Omega || !omega || !m) return fail(ORB_ERR_INVALID, "null array");
+    const long long pl = s->a.nsys * (long long)(s->a.nb - 1);
+    const size_t pb = sizeof(double) * pl;
+    cudaStream_t st = s->stream;
+    double* d_el = nullptr;
+    CU(cudaMalloc(&d_el, 6 * pb));
+    const double* src[6] = {M, e, a, inc, Omega, omega};
+    cudaError_t ce = cudaSuccess;
+    for (int k = 0; k < 6 && ce == cudaSuccess; ++k)
+        ce = cudaMemcpyAsync(d_el + k * pl, src[k], pb, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(const_cast<double*>(s->a.m), m, sizeof(double) * s->a.nsys * s->a.nb,
+                             cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = launch_ens_elements(s->a, d_el, 1e-12, 50, st);       // physics.py:43 defaults
+    EnsArgs a0 = s->a;
+    a0.nsteps = 0;
+    if (ce == cudaSuccess) ce = launch_ens_accel(a0, s->mode == ORB_MODE_FAITHFUL, st);   // engine.py:41
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d_el);
+    if (ce != cudaSuccess) return cuda_fail(ce, "orb_ens_upload_elements");
+    s->launches += 2;
+    s->have_state = true;
+    return ORB_OK;
+}
+
+int orb_kepler_states(int device, int64_t count, const double* M, const double* e, const double* a, const double* b,
+                      const double* n, const double* inc, const double* Omega, const double* omega, double tol,
+                      int max_iter, double* r3, double* v3, double* E) {
+    if (count < 0) return fail(ORB_ERR_INVALID, "negative count");
+    if (!M || !e || !a || !b || !n || !inc || !Omega || !omega || !r3 || !v3)
+        return fail(ORB_ERR_INVALID, "null array");
+    if (count == 0) return ORB_OK;
+    int rc = select_device(device);
+    if (rc) return rc;
+    const size_t pb = sizeof(double) * count;
+    double *d_el = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_el, 8 * pb));
+    cudaError_t ce = cudaMalloc(&d_out, 7 * pb);
+    const double* src[8] = {M, e, a, b, n, inc, Omega, omega};
+    for (int k = 0; k < 8 && ce == cudaSuccess; ++k)
+        ce = cudaMemcpy(d_el + k * count, src[k], pb, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = launch_kepler_states(d_el, d_out, count, tol, max_iter, nullptr);
+    if (ce == cudaSuccess) ce = cudaMemcpy(r3, d_out, 3 * pb, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(v3, d_out + 3 * count, 3 * pb, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && E) ce = cudaMemcpy(E, d_out + 6 * count, pb, cudaMemcpyDeviceToHost);
+    cudaFree(d_el);
+    cudaFree(d_out);
+    if (ce != cudaSuccess) return cuda_fail(ce, "orb_kepler_states");
+    return ORB_OK;
+}
+
 int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
     LOCK(s);
     if (!s->have_state) return fail(ORB_ERR_INVALID, "step before upload");

@@ -16,4 +16,8 @@ struct EnsArgs {
 cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st);
 cudaError_t launch_ens_accel(const EnsArgs& a, bool faithful, cudaStream_t st);
 cudaError_t launch_ens_energy(const EnsArgs& a, double* E, cudaStream_t st);
+// kepler.cu: Keplerian elements -> Cartesian state (core/physics.py:43-71, core/body.py:184-249)
+cudaError_t launch_kepler_states(const double* d_el8, double* d_out7, long long count, double tol, int max_iter,
+                                 cudaStream_t st);
+cudaError_t launch_ens_elements(const EnsArgs& a, const double* d_el6, double tol, int max_iter, cudaStream_t st);
 }  // namespace orb

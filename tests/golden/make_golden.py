@@ -269,10 +269,39 @@ def golden_kepler():
          mass=np.array([bd.mass.value for bd in system]), radius=np.array([bd.radius.value for bd in system]))
 
 
+def golden_kepler_batch(count=2048, seed=43):
+    """Random element sets through the reference's Body.get_state (core/body.py:184-249) -- the fixture the
+    batched device pipeline (orb_kepler_states / orb_ens_upload_elements) and its oracle restatement are held to."""
+    import core.body as rbody
+    import core.units as runits
+    rng = np.random.default_rng(seed)
+    sun = rbody.Body(name="Sun", a=runits.Meters(0.0), e=0.0, I=runits.Radians(0.0), L=None, M=runits.Radians(0.0),
+                     long_peri=None, long_node=runits.Radians(0.0), arg_peri=runits.Radians(0.0),
+                     mass=runits.Kilograms(1.98847e30), radius=runits.Meters(6.9634e8))
+    ecc = np.concatenate([rng.uniform(0.0, 0.97, count - 8), [0.0, 0.79999, 0.8, 0.8000001, 0.9, 0.95, 0.97, 0.5]])
+    out = {k: np.empty(count) for k in ("M", "e", "a", "b", "n", "inc", "Omega", "omega", "E")}
+    r, v = np.empty((count, 3)), np.empty((count, 3))
+    for k in range(count):
+        body = rbody.Body(name=f"p{k}", a=runits.Meters(float(np.exp(rng.uniform(np.log(0.1), np.log(40.0))) * 1.495978707e11)),
+                          e=float(ecc[k]), I=runits.Radians(float(abs(rng.normal(0.0, 0.3)))), L=None,
+                          M=runits.Radians(float(rng.uniform(0.0, 2 * np.pi))), long_peri=None,
+                          long_node=runits.Radians(float(rng.uniform(0.0, 2 * np.pi))),
+                          arg_peri=runits.Radians(float(rng.uniform(0.0, 2 * np.pi))),
+                          mass=runits.Kilograms(5.9722e24), radius=runits.Meters(6.371e6), parent=sun)
+        rr, vv = body.get_state()
+        r[k], v[k] = rr, vv
+        out["M"][k] = body.M.value; out["e"][k] = body.e; out["a"][k] = body.a.value; out["b"][k] = body.b.value
+        out["n"][k] = body.mean_motion(); out["inc"][k] = body.I.value; out["Omega"][k] = body.long_node.value
+        out["omega"][k] = body.arg_peri.value
+        out["E"][k] = rphys.solve_kepler(body.M.value, body.e)
+    save("kepler_batch", r=r, v=v, parent_mass=np.array(sun.mass.value), parent_mu=np.array(sun.mu), **out)
+
+
 def main():
     skip_disk = "--skip-disk" in sys.argv
     only = [a for a in sys.argv[1:] if not a.startswith("--")]
-    jobs = dict(ddot=golden_ddot, force=golden_force, kepler=golden_kepler, mixed=golden_mixed,
+    jobs = dict(ddot=golden_ddot, force=golden_force, kepler=golden_kepler, kepler_batch=golden_kepler_batch,
+                mixed=golden_mixed,
                 collisions=golden_collisions, solar=golden_solar, disk=golden_disk)
     for name, fn in jobs.items():
         if only and name not in only:

@@ -419,7 +419,7 @@ def test_ensemble_faithful_bit_exact_and_fast_close(nat, orc):
 def test_ensemble_odd_sizes(nat, orc):
     from core import synthetic
     from core.ensemble import EnsembleEngine
-    for nb in (2, 5, 9, 32):
+    for nb in (2, 3, 4, 5, 8, 9, 16, 17, 31, 32):
         e = synthetic.ensemble(7, nb)
         args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
         ref = {k: np.array(e[k], dtype=np.float64, copy=True) for k in ("x", "y", "z", "vx", "vy", "vz")}
@@ -431,6 +431,87 @@ def test_ensemble_odd_sizes(nat, orc):
         q = EnsembleEngine(*args, dt=e["dt"], softening=e["eps"], mode="fast"); q.step(10)
         assert np.abs(q.state()["x"] - ref["x"]).max() <= 1e-10 * np.abs(ref["x"]).max()
         f.close(); q.close()
+    # no softening, central body exactly at the origin, padded slots (nb < next power of two), more systems than
+    # one CTA holds: padded / out-of-range slots must contribute exactly nothing (no 0 * inf)
+    for nb, nsys in ((5, 67), (13, 33)):
+        e = synthetic.ensemble(nsys, nb)
+        args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
+        ref = {k: np.array(e[k], dtype=np.float64, copy=True) for k in ("x", "y", "z", "vx", "vy", "vz")}
+        orc.lib.orc_ensemble_step(nsys, nb, *(ref[k].reshape(-1) for k in ("x", "y", "z", "vx", "vy", "vz")),
+                                  np.ascontiguousarray(e["m"]).reshape(-1), e["dt"], 0.0, G, 5, 0, 0)
+        for fused in (True, False):
+            q = EnsembleEngine(*args, dt=e["dt"], softening=0.0, mode="fast"); q.step(5, fused=fused)
+            got = q.state()
+            for k in ref:
+                assert np.all(np.isfinite(got[k]))
+                assert np.abs(got[k] - ref[k]).max() <= 1e-10 * np.abs(ref[k]).max(), (nb, k, fused)
+            q.close()
+
+
+def test_kepler_states_device_vs_reference(nat, golden):
+    """Batched elements -> state on the device vs the reference's Body.get_state outputs (kepler_batch.npz).
+
+    Same operation order; only the device sin/cos can differ from the host libm, so the bar is a tolerance:
+    |dE| <= 4e-15/(1-e) and relative state error <= 1e-13 (measured ~1e-15); most entries are bit-identical."""
+    g = golden("kepler_batch")
+    r, v, E = nat.kepler_states(*(g[k] for k in ("M", "e", "a", "b", "n", "inc", "Omega", "omega")), return_E=True)
+    dE = np.abs(E - g["E"]) * (1.0 - g["e"])
+    er = np.linalg.norm(r - g["r"], axis=1) / np.linalg.norm(g["r"], axis=1)
+    ev = np.linalg.norm(v - g["v"], axis=1) / np.linalg.norm(g["v"], axis=1)
+    exact = np.mean(np.all(r == g["r"], axis=1) & np.all(v == g["v"], axis=1))
+    print(f"\nkepler batch: max |dE|(1-e) {dE.max():.2e}, max rel r {er.max():.2e}, v {ev.max():.2e}, "
+          f"bit-identical states {100 * exact:.1f} %, E {100 * np.mean(E == g['E']):.1f} %")
+    assert dE.max() <= 4e-15 and er.max() <= 1e-13 and ev.max() <= 1e-13
+    # the solve_kepler grid of the reference (kepler.npz), through the same kernel
+    k = golden("kepler")
+    MM, ee = np.meshgrid(k["kep_M"], k["kep_e"])
+    one = np.ones(MM.size)
+    _, _, E2 = nat.kepler_states(MM.ravel(), ee.ravel(), one, one, one, 0 * one, 0 * one, 0 * one, return_E=True)
+    assert np.max(np.abs(E2 - k["kep_E"].ravel()) * (1.0 - ee.ravel())) <= 4e-15
+    # host API
+    from core.datasets import solar_system_v2
+    system = solar_system_v2(moons=True)
+    system.standardize_units(mass_unit="kilograms", distance_unit="meters", angle_unit="radians", time_unit="seconds")
+    rs, vs = system.get_states()
+    assert np.allclose(rs, k["r"], rtol=1e-13, atol=0) and np.allclose(vs, k["v"], rtol=1e-13, atol=1e-20)
+
+
+def test_ensemble_generated_from_elements_on_device(nat):
+    """orb_ens_upload_elements vs the oracle restatement of the host pipeline, then a short energy-conserving run."""
+    from core.ensemble import EnsembleEngine
+    from oracle import ref_numpy
+    rng = np.random.default_rng(5)
+    nsys, nb = 48, 16
+    k = nb - 1
+    a = np.exp(rng.uniform(np.log(0.3), np.log(30.0), (nsys, k))) * 1.495978707e11
+    e = rng.uniform(0.0, 0.3, (nsys, k))
+    M, Om, om = (rng.uniform(0.0, 2 * np.pi, (nsys, k)) for _ in range(3))
+    inc = np.abs(rng.normal(0.0, np.deg2rad(2.0), (nsys, k)))
+    m = np.concatenate([np.full((nsys, 1), 1.98847e30), np.exp(rng.uniform(np.log(1e23), np.log(1e27), (nsys, k)))], 1)
+    ref = ref_numpy.ensemble_from_elements(M, e, a, inc, Om, om, m)
+    for f32 in (False, True):
+        eng = EnsembleEngine.from_elements(M, e, a, inc, Om, om, m, dt=8640.0, softening=1e6, vel_f32=f32)
+        st = eng.state()
+        for key in ("x", "y", "z"):
+            assert np.abs(st[key] - ref[key]).max() <= 1e-13 * np.abs(a).max()
+        for key in ("vx", "vy", "vz"):
+            want = ref[key].astype(np.float32).astype(np.float64) if f32 else ref[key]
+            tol = (2.0 ** -23 if f32 else 1e-13) * np.abs(ref[key]).max()
+            assert np.abs(st[key] - want).max() <= tol
+        assert np.all(st["x"][:, 0] == 0.0) and np.all(st["vx"][:, 0] == 0.0)
+        E0 = eng.energy()
+        eng.step(200)
+        drift = np.abs(eng.energy() - E0) / np.abs(E0)
+        assert drift.max() < (1e-3 if f32 else 1e-4), drift.max()       # leapfrog, >= 600 steps per orbit
+        eng.close()
+    # same state uploaded from the host -> same trajectories (generation is the only difference)
+    eng_a = EnsembleEngine.from_elements(M, e, a, inc, Om, om, m, dt=86400.0, softening=1e6)
+    s0 = eng_a.state()
+    eng_b = EnsembleEngine(s0["x"], s0["y"], s0["z"], s0["vx"], s0["vy"], s0["vz"], m, dt=86400.0, softening=1e6)
+    eng_a.step(50); eng_b.step(50)
+    sa, sb = eng_a.state(), eng_b.state()
+    assert all(np.array_equal(sa[key], sb[key]) for key in sa)
+    eng_a.close(); eng_b.close()
 
 
 def test_pairwise_accelerations_operator(golden):
