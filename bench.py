@@ -187,30 +187,43 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- ensemble side measurement
-def ensemble_measure(device, torch, nsys=65536, nbody=16, steps=200):
-    """BASELINE configs[3] on this rank: achieved HBM GB/s (one step per launch) and fused interactions/s."""
+def ensemble_measure(device, torch, nsys=65536, nbody=16, steps=200, world=1, rank=0, dist=None):
+    """BASELINE configs[3]: 65,536 independent 16-body systems, block-partitioned over the ranks with no
+    collective on the data path.  Reports achieved algorithmic GB/s with one step per launch (state round-trips
+    HBM: 152 B per body-step) and interactions/s with all steps fused in one launch; times are max over ranks."""
     from core import _native, synthetic
-    e = synthetic.ensemble_fast(nsys, nbody)
-    ens = _native.DeviceEnsemble(nsys, nbody, device, _native.MODE_FAST)
+    from core.ensemble import partition
+    lo, hi = partition(nsys, world, rank)
+    e = synthetic.ensemble_fast(hi - lo, nbody, seed=10_000 + rank)
+    ens = _native.DeviceEnsemble(hi - lo, nbody, device, _native.MODE_FAST)
     ens.set_stream(torch.cuda.current_stream().cuda_stream)
     ens.set_params(e["dt"], e["eps"], e["G"])
     ens.upload(*(e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ens.step(20, fused=False)
-    torch.cuda.synchronize()
-    ev0.record(); ens.step(steps, fused=False); ev1.record(); torch.cuda.synchronize()
-    ms_unfused = ev0.elapsed_time(ev1)
-    ens.step(20, fused=True)
-    torch.cuda.synchronize()
-    ev0.record(); ens.step(steps, fused=True); ev1.record(); torch.cuda.synchronize()
-    ms_fused = ev0.elapsed_time(ev1)
+
+    def timed(fused):
+        ens.step(20, fused=fused)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record(); ens.step(steps, fused=fused); ev1.record(); torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    ms_unfused = timed(False)
+    ms_fused = timed(True)
     ens.close()
     bytes_step = 152.0 * nsys * nbody
-    return {"workload": f"{nsys} independent {nbody}-body systems, one CTA per system",
+    return {"workload": f"{nsys} independent {nbody}-body systems, {64 // nbody} systems per warp (8 lanes each), "
+                        f"block-partitioned over {world} GPU(s), no collective",
             "unfused_gbs": bytes_step * steps / (ms_unfused * 1e-3) / 1e9,
             "unfused_system_steps_per_s": nsys * steps / (ms_unfused * 1e-3),
             "fused_interactions_per_s": nsys * nbody * nbody * steps / (ms_fused * 1e-3),
-            "bytes_per_body_step": 152, "steps": steps}
+            "bytes_per_body_step": 152, "steps": steps, "n_gpus": world}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -326,6 +339,15 @@ def run_ours(args):
            "d2h_bytes_per_step": 6 * 8 * n, "steps": e2e_steps,
            "path": "orb_upload (pinned host SoA) -> orb_step_begin/orb_accel/orb_step_kick -> orb_download_state"}
 
+    ens_result = None
+    if not args.no_ensemble:
+        try:
+            ens_result = ensemble_measure(local, torch, world=world, rank=rank, dist=dist)
+        except Exception as exc:      # never lose the headline line over the side measurement
+            if world > 1:
+                raise
+            ens_result = {"error": str(exc)}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -398,11 +420,8 @@ def run_ours(args):
         cb["note"] = ("C port of the reference algorithm on all host threads; the reference itself is single-threaded "
                       "Python at ~5-7 us per pair (BASELINE.md section 2)")
         line["cpu_baseline"] = cb
-    if world == 1 and not args.no_ensemble:
-        try:
-            line["ensemble"] = ensemble_measure(local, torch)
-        except Exception as exc:      # never lose the headline line over the side measurement
-            line["ensemble"] = {"error": str(exc)}
+    if ens_result is not None:
+        line["ensemble"] = ens_result
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -354,11 +354,13 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
     const char* env_ti = getenv("ORBITAL_B200_SYM_TI");
     // I-blocks (128*TI bodies) must be tile aligned (a multiple or a divisor of the 256-body tile), otherwise a
     // tile straddling two I-blocks would be treated one-sided by the lower block and its other bodies would miss
-    // those pairs: TI in {1, 2, 4, 6, 8}.  Measured on B200 at N=262144: TI=8 44.7 ms, TI=6 44.8 ms, TI=4 46.6 ms.
+    // those pairs: TI in {1, 2, 4, 6, 8}.  Measured on B200 (profiles/r1_sweep_n.txt): TI=8 is fastest from
+    // N=8192 up (N=262144: TI=8 39.4 ms, TI=4 41.5 ms; N=8192: 0.076 vs 0.115 ms for TI=2), TI=2 at 4096,
+    // TI=1 below.
     int ti = 8;
-    if (n < 128 * 1024) ti = 4;
-    if (n < 32 * 1024) ti = 2;
-    if (n < 8 * 1024) ti = 1;
+    if (n < 8 * 1024) ti = 4;
+    if (n < 6 * 1024) ti = 2;
+    if (n < 3 * 1024) ti = 1;
     if (env_ti) {
         const int v = atoi(env_ti);
         if (v == 1 || v == 2 || v == 4 || v == 6 || v == 8) ti = v;
