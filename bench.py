@@ -183,7 +183,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- ensemble side measurement
@@ -422,14 +422,31 @@ def run_ours(args):
         line["cpu_baseline"] = cb
     if ens_result is not None:
         line["ensemble"] = ens_result
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else any library prints (e.g. NCCL's version banner,
+    which goes to fd 1) was diverted to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)                      # stray prints of native libraries -> stderr
     if args.impl == "reference":
         run_reference(args)
     else:
