@@ -396,7 +396,8 @@ def run_ours(args):
         "kernel": info["name"], "grid": info["grid"], "block": info["block"],
         "kernel_ms": force_ms, "interactions_per_launch": local_interactions,
         "flop_per_interaction": FLOP_PER_INTERACTION,
-        "peak_source": "measured: orb_fp64_peak DFMA chain on this GPU, mean over 1 s "
+        "peak_source": "measured: orb_fp64_peak, best DFMA chain shape on this GPU (two-register form r=fma(r,a,r); "
+                       "the pipe is register-read limited, the usual fma(r,a,b) chain stops at ~91 %), mean over 1 s "
                        f"(burst {peak['tflops_best']:.2f} TF at {peak['sm_clock_mhz']:.0f} MHz); "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,

@@ -170,10 +170,16 @@ int build_graph(orb_engine* e, int steps, cudaGraphExec_t* out) {
     int rc = ensure_plan(e);   // allocations must happen outside capture
     if (rc) return rc;
     cudaGraph_t graph = nullptr;
-    CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    // capture on the library's own stream: the bound stream may be the legacy default stream, which cannot
+    // capture; the instantiated graph is launched into the bound stream
+    cudaStream_t bound = e->stream;
+    e->stream = e->own_stream;
+    cudaError_t cb = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+    if (cb != cudaSuccess) { e->stream = bound; return cuda_fail(cb, "cudaStreamBeginCapture"); }
     int launches = 0;
     for (int k = 0; k < steps && rc == ORB_OK; ++k) rc = enqueue_step(e, &launches);
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    e->stream = bound;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
     ce = cudaGraphInstantiate(out, graph, 0);
@@ -750,7 +756,36 @@ struct orb_ensemble {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     long long launches = 0;
     bool have_state = false;
+    cudaGraphExec_t step_graph = nullptr;     // kEnsGraphSteps un-fused steps (one launch each) as one graph
 };
+
+namespace {
+constexpr int kEnsGraphSteps = 16;
+
+void ens_drop_graph(orb_ensemble* s) {
+    if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
+}
+
+// small per-GPU batches make the one-step-per-launch mode launch-bound: replay 16 launches as one graph
+int ens_build_graph(orb_ensemble* s) {
+    EnsArgs a = s->a;
+    a.nsteps = 1;
+    cudaGraph_t graph = nullptr;
+    // capture on the library's own stream (the caller's may be the legacy default stream, which cannot capture);
+    // the instantiated graph is launched into whatever stream the handle is bound to
+    CU(cudaStreamBeginCapture(s->own_stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t ce = cudaSuccess;
+    for (int k = 0; k < kEnsGraphSteps && ce == cudaSuccess; ++k)
+        ce = launch_ens_step(a, s->mode == ORB_MODE_FAITHFUL, s->own_stream);
+    cudaError_t ce2 = cudaStreamEndCapture(s->own_stream, &graph);
+    if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(ce, "ensemble graph capture"); }
+    if (ce2 != cudaSuccess) return cuda_fail(ce2, "cudaStreamEndCapture");
+    ce = cudaGraphInstantiate(&s->step_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+    return ORB_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -795,6 +830,7 @@ int orb_ens_destroy(orb_ensemble* s) {
         std::lock_guard<std::mutex> lk(s->mu);
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
+        ens_drop_graph(s);
         cudaFree(s->base); cudaFree(s->d_E);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
@@ -805,6 +841,7 @@ int orb_ens_destroy(orb_ensemble* s) {
 int orb_ens_set_params(orb_ensemble* s, double dt, double eps, double G) {
     LOCK(s);
     s->a.dt = dt; s->a.h = 0.5 * dt; s->a.dt32 = (float)dt; s->a.eps2 = eps * eps; s->a.G = G;
+    ens_drop_graph(s);
     return ORB_OK;
 }
 
@@ -902,7 +939,15 @@ int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
         if (nsteps > 0) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
     } else {
         a.nsteps = 1;
-        for (int64_t k = 0; k < nsteps; ++k) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
+        int64_t k = 0;
+        if (nsteps >= kEnsGraphSteps) {
+            if (!s->step_graph) { int rc = ens_build_graph(s); if (rc) return rc; }
+            for (; k + kEnsGraphSteps <= nsteps; k += kEnsGraphSteps) {
+                CU(cudaGraphLaunch(s->step_graph, s->stream));
+                s->launches += kEnsGraphSteps;
+            }
+        }
+        for (; k < nsteps; ++k) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
     }
     return ORB_OK;
 }

@@ -448,6 +448,46 @@ def test_ensemble_odd_sizes(nat, orc):
             q.close()
 
 
+def test_graph_replay_on_the_legacy_default_stream(nat):
+    """Handles bound to the NULL stream (what torch's default stream is) still replay their CUDA graphs: capture
+    happens on the library's own stream, the launch goes to the bound stream."""
+    from core import synthetic
+    c = synthetic.random_cloud(600, seed=3)          # > 512 bodies: the kernel-sequence path that replays graphs
+    outs = []
+    for legacy in (False, True):
+        dev = nat.DeviceSystem(c.n, 0, nat.MODE_FAITHFUL)
+        if legacy:
+            dev.set_stream(0)
+        dev.set_params(c["dt"], c["eps"], G)
+        dev.upload(*c.arrays())
+        dev.accel()
+        assert dev.step(40)[0] == 40
+        outs.append(dev.download_state())
+        dev.close()
+    for k in outs[0]:
+        assert_bits(outs[0][k], outs[1][k], f"legacy-stream engine {k}")
+    e = synthetic.ensemble(40, 16)
+    res = []
+    for legacy in (False, True):
+        ens = nat.DeviceEnsemble(40, 16, 0, nat.MODE_FAST)
+        if legacy:
+            ens.set_stream(0)
+        ens.set_params(e["dt"], e["eps"], e["G"])
+        ens.upload(*(e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")))
+        ens.step(37, fused=False)                       # 2 graph replays of 16 + 5 single launches
+        res.append(ens.download())
+        ens.close()
+    ens = nat.DeviceEnsemble(40, 16, 0, nat.MODE_FAST)
+    ens.set_params(e["dt"], e["eps"], e["G"])
+    ens.upload(*(e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")))
+    ens.step(37, fused=True)
+    res.append(ens.download())
+    ens.close()
+    for k in res[0]:
+        assert_bits(res[0][k], res[1][k], f"legacy-stream ensemble {k}")
+        assert_bits(res[0][k], res[2][k], f"fused vs un-fused ensemble {k}")
+
+
 def test_kepler_states_device_vs_reference(nat, golden):
     """Batched elements -> state on the device vs the reference's Body.get_state outputs (kepler_batch.npz).
 
