@@ -622,6 +622,64 @@ __global__ void __launch_bounds__(256) potential_tree_kernel(const double4* __re
     if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 
+// Large-n potential: each unordered pair once (j > i), seed + polynomial reciprocal square root
+// (inv_r = y0 (1 + e/2 + 3/8 e^2), truncation 5/16 e^3 < 1e-17), TI targets per thread, 256-body source tiles in
+// shared memory.  A CTA is (block of 128*TI targets, slab of the tiles at or after it); tiles that overlap the
+// target block mask j <= i, the others run unmasked.  12 FP64 instructions per pair; U = -G sum_i m_i u_i.
+template <int TI>
+__global__ void __launch_bounds__(128) potential_fast_kernel(const double4* __restrict__ pos4, long long n,
+                                                             double eps2, int slabs, double* partial) {
+    __shared__ double4 tile[256];
+    __shared__ double sh[4];
+    const int b = blockIdx.x / slabs, sl = blockIdx.x - b * slabs;
+    const long long i_lo = (long long)b * 128 * TI;
+    const long long i_hi = i_lo + 128 * TI;
+    const int n_tiles = (int)((n + 255) / 256);
+    const int t_first = (int)(i_lo / 256);
+    const int per = (n_tiles - t_first + slabs - 1) / slabs;
+    const int t0 = t_first + sl * per;
+    const int t1 = min(n_tiles, t0 + per);
+    double xi[TI], yi[TI], zi[TI], u[TI];
+    long long idx[TI];
+#pragma unroll
+    for (int k = 0; k < TI; ++k) {
+        idx[k] = i_lo + (long long)k * 128 + threadIdx.x;
+        const double4 me = pos4[min(idx[k], n - 1)];
+        xi[k] = me.x; yi[k] = me.y; zi[k] = me.z;
+        u[k] = 0.0;
+    }
+    for (int t = t0; t < t1; ++t) {
+        const long long j0 = (long long)t * 256;
+        const int cnt = (int)min(256LL, n - j0);
+        for (int e = threadIdx.x; e < cnt; e += 128) tile[e] = pos4[j0 + e];
+        __syncthreads();
+        const bool masked = j0 < i_hi;
+#pragma unroll 2
+        for (int j = 0; j < cnt; ++j) {
+            const double4 q = tile[j];
+#pragma unroll
+            for (int k = 0; k < TI; ++k) {
+                const double dx = q.x - xi[k], dy = q.y - yi[k], dz = q.z - zi[k];
+                const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+                const double y0 = rsqrt_seed(r2);
+                const double e = fma(-r2, y0 * y0, 1.0);
+                double inv = fma(y0, e * fma(0.375, e, 0.5), y0);
+                if (masked) inv = (j0 + j > idx[k]) ? inv : 0.0;
+                u[k] = fma(q.w, inv, u[k]);
+            }
+        }
+        __syncthreads();
+    }
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < TI; ++k) tot += idx[k] < n ? u[k] * pos4[idx[k]].w : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) partial[blockIdx.x] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+
 __global__ void __launch_bounds__(256) final_sum_kernel(const double* __restrict__ partial, int count, int ncomp,
                                                         double scale0, double* out) {
     __shared__ double sh[8];
@@ -640,8 +698,15 @@ cudaError_t launch_potential(const DeviceState& s, const StepParams& p, bool fai
         if (launches) ++*launches;
         return cudaGetLastError();
     }
-    const int grid = grid_for(s.n, 256);
-    potential_tree_kernel<<<grid, 256, 0, st>>>(s.pos4, s.n, p.eps2, s.reduce_buf);
+    int grid = grid_for(s.n, 256);
+    if (s.n > 4096) {
+        // reduce_buf holds 4 * (ceil(n/256) + 1) partials: 8 slabs per block of 512 targets always fit
+        constexpr int kTI = 4, kSlabs = 8;
+        grid = grid_for(s.n, 128 * kTI) * kSlabs;
+        potential_fast_kernel<kTI><<<grid, 128, 0, st>>>(s.pos4, s.n, p.eps2, kSlabs, s.reduce_buf);
+    } else {
+        potential_tree_kernel<<<grid, 256, 0, st>>>(s.pos4, s.n, p.eps2, s.reduce_buf);
+    }
     final_sum_kernel<<<1, 256, 0, st>>>(s.reduce_buf, grid, 1, -p.G, d_out);
     if (launches) *launches += 2;
     return cudaGetLastError();

@@ -589,6 +589,28 @@ def test_diagnostics_device_reductions(nat, orc):
     dev.close()
 
 
+@pytest.mark.parametrize("n", [4097, 4608, 9001])
+def test_potential_large_n_kernel(nat, n):
+    """n > 4096: pair-once potential kernel (seed + polynomial 1/sqrt), ragged sizes and masses spread over eight
+    decades.  Yardstick: rows in long double (the reference-order running sum itself is only good to ~1e-11 here:
+    it drops terms below half an ulp of the partial sum)."""
+    from core import synthetic
+    c = synthetic.random_cloud(n, seed=n)
+    pos = np.stack([c["x"], c["y"], c["z"]], 1).astype(np.longdouble)
+    m = c["m"].astype(np.longdouble)
+    dev = nat.DeviceSystem(c.n, 0, nat.MODE_FAST)
+    for eps in (c["eps"], 0.0):
+        dev.set_params(c["dt"], eps, G)
+        dev.upload(*c.arrays())
+        U_ref = np.longdouble(0)
+        for i in range(n - 1):
+            d = pos[i + 1:] - pos[i]
+            U_ref -= m[i] * np.sum(m[i + 1:] / np.sqrt((d * d).sum(1) + np.longdouble(eps) ** 2))
+        U_ref = float(np.longdouble(G) * U_ref)
+        assert abs(dev.potential() - U_ref) <= 1e-13 * abs(U_ref), (n, eps)
+    dev.close()
+
+
 def test_fp64_peak_microbenchmark(nat):
     p = nat.fp64_peak(0, 0.3)
     print(f"\nFP64 DFMA peak: best {p['tflops_best']:.2f} TF, mean {p['tflops_mean']:.2f} TF at {p['sm_clock_mhz']:.0f} MHz")
