@@ -387,11 +387,14 @@ static int faithful_tw(long long n_tgt) {
     const char* env = getenv("ORBITAL_B200_FAITHFUL_TW");
     if (env) {
         const int v = atoi(env);
-        if (v == 4 || v == 8 || v == 16 || v == 32) return v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) return v;
     }
-    // measured on B200 (faithful force pass): n=4096: TW=4 0.25 ms, 8 0.31, 16 0.54, 32 0.98;
-    // n=16384: TW=4 1.80 ms, 8 1.55 (FP64-throughput bound), 16 2.34, 32 3.87
-    return n_tgt <= 8192 ? 4 : 8;
+    // measured on B200 (faithful force pass, profiles/r1_sweep_faithful.txt), ms for TW = 1 / 2 / 4 / 8:
+    //   n=1024: 0.042 0.045 0.063 0.090   n=2048: 0.087 0.084 0.111 0.167   n=4096: 0.256 0.184 0.249 0.316
+    //   n=8192: 0.937 0.562 0.527 0.710   n=16384: 3.65 2.10 1.80 1.54 (FP64-throughput bound)
+    if (n_tgt <= 1536) return 1;
+    if (n_tgt <= 6144) return 2;
+    return n_tgt <= 12288 ? 4 : 8;
 }
 
 void faithful_geometry(long long n_tgt, int* grid, int* block) {
@@ -422,6 +425,8 @@ cudaError_t launch_force_faithful(const DeviceState& s, const StepParams& p, boo
     int grid, block;
     faithful_geometry(s.tgt_hi - s.tgt_lo, &grid, &block);
     switch (faithful_tw(s.tgt_hi - s.tgt_lo)) {
+        case 1: launch_faithful_t<1>(s, p, detect, grid, st); break;
+        case 2: launch_faithful_t<2>(s, p, detect, grid, st); break;
         case 4: launch_faithful_t<4>(s, p, detect, grid, st); break;
         case 8: launch_faithful_t<8>(s, p, detect, grid, st); break;
         case 16: launch_faithful_t<16>(s, p, detect, grid, st); break;
