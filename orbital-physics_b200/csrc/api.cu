@@ -109,6 +109,20 @@ bool sym_applicable(const orb_engine* e) {
 bool acc_is_partial(const orb_engine* e) { return e->sharded && sym_applicable(e); }
 
 int ensure_plan(orb_engine* e) {
+    if (e->mode == ORB_MODE_FAITHFUL) {
+        // two-pass bit-exact force: n x ld scratch matrix of 1/r^3 (allocated outside graph capture)
+        const bool want = faithful_pairs_applicable(e->s.n, e->sharded) && !use_tiny(e);
+        if (want && !e->s.invr3) {
+            e->s.invr3_ld = faithful_pairs_ld(e->s.n);
+            const size_t bytes = sizeof(double) * (size_t)faithful_pairs_elems(e->s.n);
+            CU(cudaMalloc(&e->s.invr3, bytes));
+            CU(cudaMemsetAsync(e->s.invr3, 0, bytes, e->stream));      // padding rows / columns stay zero
+        } else if (!want && e->s.invr3) {
+            cudaFree(e->s.invr3);
+            e->s.invr3 = nullptr;
+        }
+        return ORB_OK;
+    }
     if (sym_applicable(e)) {
         if (!e->sym.valid) {
             const int world = e->sharded ? shard_world(e) : 1;
@@ -142,6 +156,8 @@ int enqueue_force(orb_engine* e, bool detect, int* launches) {
         else
             CU(launch_force_fast(e->s, e->p, e->plan, detect, e->stream, launches));
     } else {
+        int rc = ensure_plan(e);
+        if (rc) return rc;
         CU(launch_force_faithful(e->s, e->p, detect, e->stream, launches));
     }
     return ORB_OK;
@@ -217,7 +233,7 @@ void free_engine(orb_engine* e) {
     free_sym(e->sym);
     cudaFree(e->s.pos4); cudaFree(e->s.vel); cudaFree(e->s.acc); cudaFree(e->s.radius); cudaFree(e->s.vf32);
     cudaFree(e->s.ctl); cudaFree(e->s.pairs); cudaFree(e->s.hist); cudaFree(e->s.scratch);
-    cudaFree(e->s.reduce_buf); cudaFree(e->d_stage); cudaFree(e->d_diag);
+    cudaFree(e->s.reduce_buf); cudaFree(e->d_stage); cudaFree(e->d_diag); cudaFree(e->s.invr3);
     if (e->h_diag) cudaFreeHost(e->h_diag);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -652,9 +668,11 @@ int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, in
             lps = 4 + (e->plan.slabs > 1 ? 1 : 0);
         }
     } else {
-        nm = "force_faithful_kernel";
+        const bool two_pass = faithful_pairs_applicable(e->s.n, e->sharded);
+        nm = two_pass ? "faithful_pairs_kernel+faithful_rows_kernel" : "force_faithful_kernel";
         faithful_geometry(e->s.tgt_hi - e->s.tgt_lo, &g, &b);
         sm = b * 40;
+        if (two_pass) lps = 5;
     }
     if (name && name_len > 0) { strncpy(name, nm, name_len - 1); name[name_len - 1] = 0; }
     if (grid) *grid = g;

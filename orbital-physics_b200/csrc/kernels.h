@@ -24,6 +24,8 @@ struct DeviceState {
     double* scratch = nullptr;      // fast kernel partial sums: slabs x 3 x n_tgt
     long long scratch_elems = 0;
     double* reduce_buf = nullptr;   // diagnostics partials
+    double* invr3 = nullptr;        // faithful two-pass path: n x invr3_ld matrix of 1/r^3 (both triangles)
+    long long invr3_ld = 0;
 };
 
 struct StepParams {
@@ -55,6 +57,10 @@ cudaError_t launch_force_fast(const DeviceState& s, const StepParams& p, const F
 cudaError_t launch_force_faithful(const DeviceState& s, const StepParams& p, bool detect, cudaStream_t st,
                                   int* launches);
 void faithful_geometry(long long n_tgt, int* grid, int* block);
+// two-pass bit-exact force (pair matrix of 1/r^3, then ordered row sums): sizes it is used for, leading dimension
+bool faithful_pairs_applicable(long long n, bool sharded);
+long long faithful_pairs_ld(long long n);
+long long faithful_pairs_elems(long long n);
 const char* fast_kernel_name(int ti, bool detect);
 
 // ---- integrate.cu ----

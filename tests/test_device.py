@@ -224,6 +224,32 @@ def test_force_fast_plummer_262144_sampled_rows(nat, orc):
     dev.close()
 
 
+@pytest.mark.parametrize("n", [513, 1500, 4099])
+def test_force_faithful_two_pass_equals_one_pass(nat, n, monkeypatch):
+    """512 < n <= 32768: pair matrix of 1/r^3 (each pair's sqrt/div once) + ordered row sums; must be bit-identical
+    to the one-pass kernel, including the overlap list."""
+    from core import synthetic
+    c = synthetic.random_cloud(n, seed=77 + n, radius=2.5e9)       # radii large enough for a few hundred overlaps
+    out = []
+    for pairs in ("1", "0"):
+        monkeypatch.setenv("ORBITAL_B200_FAITHFUL_PAIRS", pairs)
+        dev = nat.DeviceSystem(c.n, 0, nat.MODE_FAITHFUL)
+        dev.set_params(c["dt"], 0.0, G)
+        dev.upload(*c.arrays())
+        dev.accel()
+        name = dev.force_kernel_info()["name"]
+        assert ("faithful_pairs_kernel" in name) == (pairs == "1"), name
+        a = dev.download_acc()
+        done, nov = dev.step(1)
+        pl, cnt = dev.overlap_pairs()
+        out.append((a, dev.download_state(), sorted(map(tuple, pl.tolist())), cnt))
+        dev.close()
+    assert_bits(out[0][0], out[1][0], "acc")
+    for k in out[0][1]:
+        assert_bits(out[0][1][k], out[1][1][k], f"state {k}")
+    assert out[0][3] == out[1][3] and out[0][2] == out[1][2] and out[0][3] > 0
+
+
 @pytest.mark.parametrize("n", [600, 1500])
 def test_step_faithful_kernel_sequence_bit_exact(nat, orc, n):
     """n > 512 takes the multi-kernel CUDA-graph path; n = 600 also has radii -> overlap detection on."""

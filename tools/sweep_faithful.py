@@ -14,8 +14,9 @@ for n in (1024, 2048, 4096, 8192, 16384):
     c = synthetic.uniform_disk(n) if hasattr(synthetic, "uniform_disk") else synthetic.random_cloud(n, seed=n)
     row = [f"N={n:6d}"]
     ref = None
-    for tw in (1, 2, 4, 8):
+    for tw, pairs in ((1, "0"), (2, "0"), (4, "0"), (8, "0"), (0, "1")):
         os.environ["ORBITAL_B200_FAITHFUL_TW"] = str(tw)
+        os.environ["ORBITAL_B200_FAITHFUL_PAIRS"] = pairs
         dev = _native.DeviceSystem(n, 0, _native.MODE_FAITHFUL)
         dev.set_stream(torch.cuda.current_stream().cuda_stream)
         dev.set_params(c["dt"], c["eps"], c["G"]); dev.upload(*c.arrays()); dev.accel(); dev.accel()
@@ -28,6 +29,6 @@ for n in (1024, 2048, 4096, 8192, 16384):
         if ref is None:
             ref = acc
         same = np.array_equal(acc, ref)
-        row.append(f"TW={tw}: {np.median(ts):8.4f} ms{'' if same else ' MISMATCH'}")
+        row.append(f"{'2pass ' if pairs == '1' else ''}TW={tw}: {np.median(ts):7.4f}{'' if same else ' MISMATCH'}")
         dev.close()
     print("  ".join(row), flush=True)
