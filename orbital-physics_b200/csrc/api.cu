@@ -66,6 +66,7 @@ struct orb_engine {
     bool plan_valid = false;
     SymPlan sym;                     // pair-symmetric kernel (unsharded fast mode)
     bool use_sym = true;
+    bool pairs_unavailable = false;  // the two-pass faithful force could not allocate its pair matrix
     bool detect = false;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -111,11 +112,17 @@ bool acc_is_partial(const orb_engine* e) { return e->sharded && sym_applicable(e
 int ensure_plan(orb_engine* e) {
     if (e->mode == ORB_MODE_FAITHFUL) {
         // two-pass bit-exact force: n x ld scratch matrix of 1/r^3 (allocated outside graph capture)
-        const bool want = faithful_pairs_applicable(e->s.n, e->sharded) && !use_tiny(e);
+        const bool want = faithful_pairs_applicable(e->s.n, e->sharded) && !use_tiny(e) && !e->pairs_unavailable;
         if (want && !e->s.invr3) {
             e->s.invr3_ld = faithful_pairs_ld(e->s.n);
             const size_t bytes = sizeof(double) * (size_t)faithful_pairs_elems(e->s.n);
-            CU(cudaMalloc(&e->s.invr3, bytes));
+            if (cudaMalloc(&e->s.invr3, bytes) != cudaSuccess) {
+                // no room for the 8 n^2-byte pair matrix: the one-pass kernel computes the same bits
+                cudaGetLastError();
+                e->s.invr3 = nullptr;
+                e->pairs_unavailable = true;
+                return ORB_OK;
+            }
             CU(cudaMemsetAsync(e->s.invr3, 0, bytes, e->stream));      // padding rows / columns stay zero
         } else if (!want && e->s.invr3) {
             cudaFree(e->s.invr3);
@@ -668,7 +675,7 @@ int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, in
             lps = 4 + (e->plan.slabs > 1 ? 1 : 0);
         }
     } else {
-        const bool two_pass = faithful_pairs_applicable(e->s.n, e->sharded);
+        const bool two_pass = faithful_pairs_applicable(e->s.n, e->sharded) && !e->pairs_unavailable;
         nm = two_pass ? "faithful_pairs_kernel+faithful_rows_kernel" : "force_faithful_kernel";
         faithful_geometry(e->s.tgt_hi - e->s.tgt_lo, &g, &b);
         sm = b * 40;
