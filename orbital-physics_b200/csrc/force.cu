@@ -443,16 +443,22 @@ __global__ void __launch_bounds__(256) faithful_pairs_kernel(const double4* __re
 // started at +0.0; the diagonal entry is 0 for the same reason.  No predicates in the loop.
 // (A variant with one component of one target per lane -- 4 FP64 instructions per source instead of 10, four warps
 // per block -- was slower: 0.154 vs 0.128 ms at n = 4096, 1.75 vs 0.91 ms at n = 16384.)
-constexpr int kRowStages = 4;
+#ifndef ORB_ROW_STAGES
+#define ORB_ROW_STAGES 4
+#endif
+constexpr int kRowStages = ORB_ROW_STAGES;       // x 9 KiB of shared memory (8 or 16 stages: no faster at n = 4096,
+                                                 // slower at n = 16384 where they cut the resident CTAs per SM)
+constexpr int kRowSmem = kRowStages * (8192 + 1024) + 1024 + 64;
 
 __global__ void __launch_bounds__(32) faithful_rows_kernel(const double4* __restrict__ pos4,
                                                            const double* __restrict__ invr3, double* acc, long long n,
                                                            long long n_rows, double G, const Ctl* ctl) {
     if (ctl->halted) return;
-    __shared__ __align__(128) double mt[kRowStages][32 * 32];   // slabs of the matrix
-    __shared__ __align__(128) double4 praw[kRowStages][32];     // the slabs' source bodies {x, y, z, m}
-    __shared__ double4 sp[32];                                  // ... as {x, y, z, G*m}
-    __shared__ uint64_t full[kRowStages];
+    extern __shared__ __align__(128) unsigned char rows_smem[];
+    double (*mt)[32 * 32] = reinterpret_cast<double (*)[32 * 32]>(rows_smem);                  // slabs of the matrix
+    double4 (*praw)[32] = reinterpret_cast<double4 (*)[32]>(rows_smem + kRowStages * 8192);    // their source bodies
+    double4* sp = reinterpret_cast<double4*>(rows_smem + kRowStages * (8192 + 1024));          // ... as {x,y,z,G*m}
+    uint64_t* full = reinterpret_cast<uint64_t*>(rows_smem + kRowStages * (8192 + 1024) + 1024);
     const int lane = threadIdx.x;
     const long long i = blockIdx.x * 32LL + lane;
     const double4 me = pos4[min(i, n - 1)];
@@ -551,7 +557,12 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
         else
             faithful_pairs_kernel<false><<<dim3(nb, nb), dim3(32, 8), 0, st>>>(s.pos4, s.radius, s.invr3, s.n,
                                                                                s.invr3_ld, p.eps2, s.ctl, s.pairs);
-        faithful_rows_kernel<<<nb, 32, 0, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl);
+        static bool rows_attr = false;
+        if (!rows_attr) {
+            cudaFuncSetAttribute(faithful_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
+            rows_attr = true;
+        }
+        faithful_rows_kernel<<<nb, 32, kRowSmem, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl);
         return;
     }
     if (detect)
