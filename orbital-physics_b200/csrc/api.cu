@@ -91,7 +91,7 @@ void drop_graphs(orb_engine* e) {
 }
 
 bool use_tiny(const orb_engine* e) {
-    return e->mode == ORB_MODE_FAITHFUL && !e->sharded && e->s.n <= kTinyMax;
+    return e->mode == ORB_MODE_FAITHFUL && !e->sharded && e->s.n <= tiny_limit();
 }
 
 // world / rank of a sharded engine with equal slabs (0 when the slabs are not equal)

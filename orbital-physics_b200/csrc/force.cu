@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(32) faithful_rows_kernel(const double4* __rest
 bool faithful_pairs_applicable(long long n, bool sharded) {
     const char* env = getenv("ORBITAL_B200_FAITHFUL_PAIRS");     // "0": always the one-pass kernel (cross-check)
     if (env && env[0] == '0') return false;
-    return !sharded && n > kTinyMax && n <= 32768;               // 8 n^2 bytes of scratch: 8 GiB at n = 32768
+    return !sharded && n > tiny_limit() && n <= 32768;               // 8 n^2 bytes of scratch: 8 GiB at n = 32768
 }
 
 long long faithful_pairs_ld(long long n) { return (n + 31) / 32 * 32; }

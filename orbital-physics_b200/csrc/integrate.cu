@@ -9,6 +9,8 @@
 #include <cstdio>
 
 #include "contacts.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace orb {
@@ -326,6 +328,16 @@ __global__ void __launch_bounds__(512, 1) tiny_steps_kernel(double4* pos4, doubl
 // paid n(n-1)/2 times instead of n(n-1), spread over all lanes of the CTA.
 // ---------------------------------------------------------------------------
 constexpr int kMicroMax = 64;
+
+// One CTA for the whole system saves every launch but uses one SM.  Measured (profiles/r1_sweep_tiny.txt, us per
+// step): micro_steps_kernel 0.76 (n=15) ... 3.3 (n=64) against ~10 for the multi-CTA kernel sequence (two-pass force
+// under a CUDA graph), but tiny_steps_kernel 25 (n=65) ... 1256 (n=512) against 10.7 ... 19.4: the fused path is the
+// default only up to kMicroMax.  ORBITAL_B200_TINY_MAX (<= kTinyMax) moves the limit (cross-checks).
+int tiny_limit() {
+    const char* env = getenv("ORBITAL_B200_TINY_MAX");
+    const int v = env ? atoi(env) : kMicroMax;
+    return v < 0 ? 0 : (v > kTinyMax ? kTinyMax : v);
+}
 
 template <bool DETECT>
 __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, double* vel, double* acc,

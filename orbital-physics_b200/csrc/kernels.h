@@ -72,7 +72,8 @@ cudaError_t launch_contacts(const DeviceState& s, const StepParams& p, bool orde
                             int* launches);
 cudaError_t launch_hist_append(const DeviceState& s, cudaStream_t st);
 // single-CTA fused multi-step kernel (faithful arithmetic), n <= kTinyMax
-constexpr int kTinyMax = 512;
+constexpr int kTinyMax = 512;        // capacity of the fused kernels
+int tiny_limit();                    // sizes that actually take them (<= kTinyMax; ORBITAL_B200_TINY_MAX overrides)
 int tiny_block(int n);
 cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long long nsteps, bool detect,
                               cudaStream_t st);

@@ -224,6 +224,37 @@ def test_force_fast_plummer_262144_sampled_rows(nat, orc):
     dev.close()
 
 
+@pytest.mark.parametrize("n", [65, 100, 300, 512])
+def test_fused_single_cta_kernel_equals_kernel_sequence(nat, orc, n, monkeypatch):
+    """64 < n <= 512: the multi-CTA kernel sequence is the default (10-19 us/step against 25-1256 for the fused
+    tiny_steps_kernel); both must produce the oracle's bits, history ring included."""
+    from core import synthetic
+    from oracle.c_oracle import State
+    c = synthetic.random_cloud(n, seed=500 + n)
+    K = 12
+    st = State(orc, c["x"], c["y"], c["z"], c["vx"], c["vy"], c["vz"], c["m"], c["radius"], 0, c["dt"], c["eps"])
+    st.step(K)
+    for limit, kernel in (("512", "tiny_steps_kernel"), (None, "faithful_pairs_kernel")):
+        if limit:
+            monkeypatch.setenv("ORBITAL_B200_TINY_MAX", limit)
+        else:
+            monkeypatch.delenv("ORBITAL_B200_TINY_MAX", raising=False)
+        dev = nat.DeviceSystem(c.n, 0, nat.MODE_FAITHFUL)
+        dev.set_params(c["dt"], c["eps"], G)
+        dev.set_history(4)
+        dev.upload(*c.arrays())
+        dev.accel()
+        assert kernel in dev.force_kernel_info()["name"]
+        assert dev.step(K)[0] == K
+        s = dev.download_state()
+        assert_bits(np.stack([s["x"], s["y"], s["z"]], 1), st.pos, f"{kernel} positions")
+        assert_bits(np.stack([s["vx"], s["vy"], s["vz"]], 1), st.vel, f"{kernel} velocities")
+        h = dev.history_download(4)
+        assert h.shape[0] == 4
+        assert_bits(h[-1], st.pos, f"{kernel} last history point")
+        dev.close()
+
+
 @pytest.mark.parametrize("n", [513, 1500, 4099])
 def test_force_faithful_two_pass_equals_one_pass(nat, n, monkeypatch):
     """512 < n <= 32768: pair matrix of 1/r^3 (each pair's sqrt/div once) + ordered row sums; must be bit-identical
