@@ -174,11 +174,21 @@ int enqueue_force(orb_engine* e, bool detect, int* launches) {
 int enqueue_step(orb_engine* e, int* launches) {
     CU(launch_kick_drift(e->s, e->p, e->stream));
     ++*launches;
+    const bool contacts_here = e->p.device_contacts && e->detect;
+    if (e->mode == ORB_MODE_FAITHFUL && !contacts_here) {
+        int rc = ensure_plan(e);
+        if (rc) return rc;
+        if (e->s.invr3) {
+            // two-pass bit-exact force with the rest of the step fused into its second pass: three launches
+            CU(launch_force_faithful(e->s, e->p, e->detect, e->stream, launches, true));
+            return ORB_OK;
+        }
+    }
     int rc = enqueue_force(e, e->detect, launches);
     if (rc) return rc;
     CU(launch_kick_hist(e->s, e->p, e->stream));
     ++*launches;
-    if (e->p.device_contacts && e->detect) {
+    if (contacts_here) {
         // engine.py:85: contacts after the second half-kick -- resolved on the device, the step never halts
         const bool ordered_u = e->mode == ORB_MODE_FAITHFUL && e->s.n <= 4096;
         CU(launch_contacts(e->s, e->p, ordered_u, e->stream, launches));
@@ -679,7 +689,7 @@ int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, in
         nm = two_pass ? "faithful_pairs_kernel+faithful_rows_kernel" : "force_faithful_kernel";
         faithful_geometry(e->s.tgt_hi - e->s.tgt_lo, &g, &b);
         sm = b * 40;
-        if (two_pass) lps = 5;
+        if (two_pass) lps = (e->p.device_contacts && e->detect) ? 5 : 3;     // step tail fused into pass 2
     }
     if (name && name_len > 0) { strncpy(name, nm, name_len - 1); name[name_len - 1] = 0; }
     if (grid) *grid = g;

@@ -23,6 +23,8 @@ struct Ctl {
     int u_valid;              // u_stash holds U of the last force build (stashed before contacts moved bodies)
     double u_stash;
     long long contacts_total; // touching pairs resolved on the device since the last orb_step began
+    unsigned int rows_done;   // CTAs of faithful_rows_kernel<true> that finished their tail (last one advances)
+    int pad_;
 };
 
 constexpr int kOverlapCap = 1 << 16;   // recorded pairs per halting step

@@ -450,9 +450,21 @@ constexpr int kRowStages = ORB_ROW_STAGES;       // x 9 KiB of shared memory (8 
                                                  // slower at n = 16384 where they cut the resident CTAs per SM)
 constexpr int kRowSmem = kRowStages * (8192 + 1024) + 1024 + 64;
 
+// FUSE_TAIL: the rest of the leapfrog step rides along -- second half-kick (engine.py:81-82), history append
+// (engine.py:88-92) and, by the last CTA to finish, the step bookkeeping of advance_kernel -- which takes the step
+// from five launches to three (what counts below a few thousand bodies, where a step is launch latency).
+struct RowsTail {
+    double* vel;
+    const uint8_t* vf32;
+    double* hist;
+    long long hist_cap;
+    double h;
+};
+
+template <bool FUSE_TAIL>
 __global__ void __launch_bounds__(32) faithful_rows_kernel(const double4* __restrict__ pos4,
                                                            const double* __restrict__ invr3, double* acc, long long n,
-                                                           long long n_rows, double G, const Ctl* ctl) {
+                                                           long long n_rows, double G, Ctl* ctl, const RowsTail tail) {
     if (ctl->halted) return;
     extern __shared__ __align__(128) unsigned char rows_smem[];
     double (*mt)[32 * 32] = reinterpret_cast<double (*)[32 * 32]>(rows_smem);                  // slabs of the matrix
@@ -507,6 +519,30 @@ __global__ void __launch_bounds__(32) faithful_rows_kernel(const double4* __rest
         acc[i + n] = by;
         acc[i + 2 * n] = bz;
     }
+    if (FUSE_TAIL) {
+        if (i < n) {
+            const bool f32 = tail.vf32[i] != 0;
+            tail.vel[i] = kick_faithful(tail.vel[i], tail.h, bx, f32);
+            tail.vel[i + n] = kick_faithful(tail.vel[i + n], tail.h, by, f32);
+            tail.vel[i + 2 * n] = kick_faithful(tail.vel[i + 2 * n], tail.h, bz, f32);
+            if (tail.hist_cap > 0 && ctl->overlap_count == 0) {            // a halting step appends on the host
+                double* row = tail.hist + ((ctl->hist_count % tail.hist_cap) * n + i) * 3;
+                row[0] = me.x; row[1] = me.y; row[2] = me.z;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(&ctl->rows_done, 1u) == gridDim.x - 1) {         // every CTA has read hist_count by now
+                ctl->rows_done = 0;
+                ctl->steps_done += 1;
+                if (ctl->overlap_count > 0)
+                    ctl->halted = 1;
+                else if (tail.hist_cap > 0)
+                    ctl->hist_count += 1;
+            }
+        }
+    }
 }
 
 bool faithful_pairs_applicable(long long n, bool sharded) {
@@ -540,7 +576,8 @@ void faithful_geometry(long long n_tgt, int* grid, int* block) {
 }
 
 template <int TW>
-static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool detect, int grid, cudaStream_t st) {
+static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool detect, int grid, cudaStream_t st,
+                              bool fuse_tail) {
     const int smem = kFaithWarps * (3 * TW * 33 * 8 + TW * 32);
     static bool attr_set = false;
     if (!attr_set) {
@@ -559,10 +596,17 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
                                                                                s.invr3_ld, p.eps2, s.ctl, s.pairs);
         static bool rows_attr = false;
         if (!rows_attr) {
-            cudaFuncSetAttribute(faithful_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
+            cudaFuncSetAttribute(faithful_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
+            cudaFuncSetAttribute(faithful_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
             rows_attr = true;
         }
-        faithful_rows_kernel<<<nb, 32, kRowSmem, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl);
+        const RowsTail tail = {s.vel, s.vf32, s.hist, s.hist_cap, p.h};
+        if (fuse_tail)
+            faithful_rows_kernel<true><<<nb, 32, kRowSmem, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl,
+                                                                tail);
+        else
+            faithful_rows_kernel<false><<<nb, 32, kRowSmem, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl,
+                                                                 tail);
         return;
     }
     if (detect)
@@ -574,16 +618,17 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
 }
 
 cudaError_t launch_force_faithful(const DeviceState& s, const StepParams& p, bool detect, cudaStream_t st,
-                                  int* launches) {
+                                  int* launches, bool fuse_tail) {
+    if (fuse_tail && !s.invr3) return cudaErrorInvalidValue;      // only the two-pass path carries the step tail
     int grid, block;
     faithful_geometry(s.tgt_hi - s.tgt_lo, &grid, &block);
     switch (faithful_tw(s.tgt_hi - s.tgt_lo)) {
-        case 1: launch_faithful_t<1>(s, p, detect, grid, st); break;
-        case 2: launch_faithful_t<2>(s, p, detect, grid, st); break;
-        case 4: launch_faithful_t<4>(s, p, detect, grid, st); break;
-        case 8: launch_faithful_t<8>(s, p, detect, grid, st); break;
-        case 16: launch_faithful_t<16>(s, p, detect, grid, st); break;
-        default: launch_faithful_t<32>(s, p, detect, grid, st); break;
+        case 1: launch_faithful_t<1>(s, p, detect, grid, st, fuse_tail); break;
+        case 2: launch_faithful_t<2>(s, p, detect, grid, st, fuse_tail); break;
+        case 4: launch_faithful_t<4>(s, p, detect, grid, st, fuse_tail); break;
+        case 8: launch_faithful_t<8>(s, p, detect, grid, st, fuse_tail); break;
+        case 16: launch_faithful_t<16>(s, p, detect, grid, st, fuse_tail); break;
+        default: launch_faithful_t<32>(s, p, detect, grid, st, fuse_tail); break;
     }
     if (launches) *launches += s.invr3 ? 2 : 1;
     return cudaGetLastError();

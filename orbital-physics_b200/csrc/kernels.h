@@ -54,8 +54,10 @@ struct FastPlan {
 FastPlan plan_fast(long long n_tgt, long long n_src, int sm_count);
 cudaError_t launch_force_fast(const DeviceState& s, const StepParams& p, const FastPlan& plan, bool detect,
                               cudaStream_t st, int* launches);
+// fuse_tail (two-pass path only, s.invr3 != nullptr): second half-kick, history append and step bookkeeping ride
+// along in the force pass (replaces launch_kick_hist + launch_advance)
 cudaError_t launch_force_faithful(const DeviceState& s, const StepParams& p, bool detect, cudaStream_t st,
-                                  int* launches);
+                                  int* launches, bool fuse_tail = false);
 void faithful_geometry(long long n_tgt, int* grid, int* block);
 // two-pass bit-exact force (pair matrix of 1/r^3, then ordered row sums): sizes it is used for, leading dimension
 bool faithful_pairs_applicable(long long n, bool sharded);

@@ -308,7 +308,7 @@ def test_step_faithful_kernel_sequence_bit_exact(nat, orc, n):
     h = dev.history_download(8)
     assert h.shape == (8, n, 3)
     assert_bits(h[-1], st.pos, "last ring entry")
-    assert dev.launch_count() > 24 * 4
+    assert dev.launch_count() >= 24 * 3          # kick_drift + pair matrix + (ordered rows, kick, history, bookkeeping)
     dev.close()
 
 
