@@ -178,7 +178,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "n_bodies": n, "interactions_per_step": "N^2 (extrapolated from the sample)"},
+        "config": {"workload": name, "n_bodies": n, "mode": "reference rounding sequence (CPU port, row form)",
+                   "ic": "Plummer (Aarseth-Henon-Wielen), seed=N",
+                   "interactions_per_step": "N^2 (extrapolated from the bounded row sample)",
+                   "l2": "n/a (CPU)", "parallelism": f"{threads} host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
