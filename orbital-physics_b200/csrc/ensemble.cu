@@ -36,33 +36,28 @@ __device__ __forceinline__ double ens_drift(double r, double v, double dt, float
     return __dadd_rn(r, __dmul_rn(v, dt));
 }
 
-// One warp per system; `blockDim.x / 32` systems per CTA (1 = one CTA per system).
+// Faithful mode.  One warp per system; `blockDim.x / 32` systems per CTA (1 = one CTA per system); lane i owns
+// body i and adds its terms in ascending j with the reference's rounding sequence.
 // NBP = bodies rounded up to a power of two (compile time: loops fully unrolled, no index arithmetic).
-template <bool FAITHFUL, int NBP, bool F32>
+template <int NBP, bool F32>
 __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsArgs g) {
-    __shared__ double4 sp_all[kEnsMaxWarps][NBP];   // {x,y,z,m or G*m}
+    __shared__ double4 sp_all[kEnsMaxWarps][NBP];   // {x, y, z, G*m}
     const int warp = threadIdx.x >> 5;
     double4* sp = sp_all[warp];
-    const int sys = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (sys >= (int)g.nsys) return;                 // whole warp exits together
-    const int lane = threadIdx.x & 31;
-    // lanes sharing one body in fast mode: 32/NBP, but never more than there are sources
-    constexpr int NPARTS = FAITHFUL ? 1 : ((32 / NBP) < NBP ? (32 / NBP) : NBP);
-    constexpr int NSRC = NBP / NPARTS;                      // sources per lane
-    const int i = FAITHFUL ? lane : (lane & (NBP - 1));
-    const int part = FAITHFUL ? 0 : lane / NBP;
+    const long long sys = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (sys >= g.nsys) return;                      // whole warp exits together
+    const int i = threadIdx.x & 31;
     const int nb = g.nb;
     const bool body = i < nb;
-    const bool owner = body && (part == 0);         // lane that stores body i
-    const int o = sys * nb + i;
+    const long long o = sys * nb + i;
 
     double x = 0, y = 0, z = 0, m = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0;
-    if (body) {                                     // replicas load the same lines (L1 hit)
+    if (body) {
         x = g.x[o]; y = g.y[o]; z = g.z[o]; m = g.m[o];
         vx = g.vx[o]; vy = g.vy[o]; vz = g.vz[o];
         ax = g.ax[o]; ay = g.ay[o]; az = g.az[o];
     }
-    const double mw = FAITHFUL ? __dmul_rn(g.G, m) : m;
+    const double gm = __dmul_rn(g.G, m);            // G * m (physics.py:151-152)
     const double h = g.h, dt = g.dt, eps2 = g.eps2;
     const float dt32 = g.dt32;
 
@@ -73,41 +68,16 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsAr
         x = ens_drift<F32>(x, vx, dt, dt32);                      // engine.py:73-75
         y = ens_drift<F32>(y, vy, dt, dt32);
         z = ens_drift<F32>(z, vz, dt, dt32);
-        if (lane < NBP) sp[lane] = make_double4(x, y, z, body ? mw : 0.0);   // padded bodies: zero mass
+        if (i < NBP) sp[i] = make_double4(x, y, z, gm);
         __syncwarp();
-        double bx = 0.0, by = 0.0, bz = 0.0;
-        if (FAITHFUL) {
-            if (body) {
+        double bx = 0.0, by = 0.0, bz = 0.0;                      // physics.py:132
+        if (body) {
 #pragma unroll
-                for (int j = 0; j < NBP; ++j) {
-                    if (j == i || j >= nb) continue;
-                    const double4 q = sp[j];
-                    pair_faithful(__dsub_rn(q.x, x), __dsub_rn(q.y, y), __dsub_rn(q.z, z), eps2, q.w, bx, by, bz);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int jj = 0; jj < NSRC; ++jj) {
-                if (part >= NPARTS) break;                        // tiny systems: surplus lanes contribute zero
-                const int j = jj * NPARTS + part;
+            for (int j = 0; j < NBP; ++j) {
+                if (j == i || j >= nb) continue;
                 const double4 q = sp[j];
-                const double dx = q.x - x, dy = q.y - y, dz = q.z - z;
-                const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
-                const double y0 = rsqrt_seed(r2);
-                const double u = y0 * y0;
-                const double e = fma(-r2, u, 1.0);
-                const double w = (q.w * y0) * u;
-                double sc = fma(w, e * fma(1.875, e, 1.5), w);
-                sc = (j == i) ? 0.0 : sc;                         // self pair (also kills the eps = 0 NaN)
-                bx = fma(sc, dx, bx); by = fma(sc, dy, by); bz = fma(sc, dz, bz);
+                pair_faithful(__dsub_rn(q.x, x), __dsub_rn(q.y, y), __dsub_rn(q.z, z), eps2, q.w, bx, by, bz);
             }
-#pragma unroll
-            for (int off = NBP; off < 32; off <<= 1) {            // combine the lanes sharing a body
-                bx += __shfl_xor_sync(0xffffffffu, bx, off);
-                by += __shfl_xor_sync(0xffffffffu, by, off);
-                bz += __shfl_xor_sync(0xffffffffu, bz, off);
-            }
-            bx *= g.G; by *= g.G; bz *= g.G;
         }
         ax = bx; ay = by; az = bz;
         vx = ens_kick<F32>(vx, h, ax);                            // engine.py:81-82
@@ -115,7 +85,7 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsAr
         vz = ens_kick<F32>(vz, h, az);
         __syncwarp();
     }
-    if (owner) {
+    if (body) {
         g.x[o] = x; g.y[o] = y; g.z[o] = z;
         g.vx[o] = vx; g.vy[o] = vy; g.vz[o] = vz;
         g.ax[o] = ax; g.ay[o] = ay; g.az[o] = az;
@@ -341,9 +311,9 @@ static void launch_ens_step_t(const EnsArgs& a, int w, cudaStream_t st) {
     if (FAITHFUL) {
         const unsigned grid = (unsigned)((a.nsys + w - 1) / w);                 // one warp per system
         if (a.vel_f32)
-            ens_step_kernel<true, NBP, true><<<grid, block, 0, st>>>(a);
+            ens_step_kernel<NBP, true><<<grid, block, 0, st>>>(a);
         else
-            ens_step_kernel<true, NBP, false><<<grid, block, 0, st>>>(a);
+            ens_step_kernel<NBP, false><<<grid, block, 0, st>>>(a);
     } else {
         const long long per_cta = (long long)w * (64 / NBP);                    // 64/NBP systems per warp
         const unsigned grid = (unsigned)((a.nsys + per_cta - 1) / per_cta);
