@@ -205,7 +205,7 @@ static int occupancy_for(int ti) {
 }
 
 const char* fast_kernel_name(int ti, bool detect) {
-    static char buf[64];
+    static thread_local char buf[64];
     snprintf(buf, sizeof buf, "force_fast_kernel<%d,%s>", ti, detect ? "true" : "false");
     return buf;
 }

@@ -334,7 +334,7 @@ static cudaError_t launch_sym_t(const SymArgs& a, int grid, cudaStream_t st) {
 }
 
 const char* sym_kernel_name(int ti, bool detect, bool uniform) {
-    static char buf[64];
+    static thread_local char buf[64];
     snprintf(buf, sizeof buf, "force_sym_kernel<%d,%s,%s>", ti, detect ? "true" : "false", uniform ? "true" : "false");
     return buf;
 }
