@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
     unsigned long long* cscratch = reinterpret_cast<unsigned long long*>(cterms + 256);
     unsigned short* plist = reinterpret_cast<unsigned short*>(cscratch + 4);   // (i << 8) | j, i < j
     bool u_set = false;
-    if (threadIdx.x == 0) ctl->u_valid = 0;
+    __shared__ volatile int hitflag[2];
+    if (threadIdx.x == 0) { ctl->u_valid = 0; hitflag[0] = 0; hitflag[1] = 0; }
     const int tid = threadIdx.x;
     const int npairs = n * (n - 1) / 2;
     for (int p = tid; p < npairs; p += blockDim.x) {        // lexicographic pair list: p -> (i, j), i < j
@@ -399,12 +400,13 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             sp[tid] = make_double4(x, y, z, gm);
         }
         __syncthreads();
-        int hit = 0;
         for (int p = tid; p < npairs; p += blockDim.x) {            // physics.py:136-155, one pair per lane
             const int code = (p == tid) ? first_pair : plist[p];
             const int i = code >> 8, j = code & 0xff;
             const double4 pi = sp[i], pj = sp[j];
             const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y), dz = __dsub_rn(pj.z, pi.z);  // :145
+            // physics.py:517-518 (ri - rj): tested up front so that it overlaps the sqrt / divide chain below
+            const bool touching = DETECT && overlap_exact(-dx, -dy, -dz, sr[i], sr[j]);
             const double r2 = __dadd_rn(dot3_numpy(dx, dy, dz), eps2);                                        // :146
             const double inv_r = __ddiv_rn(1.0, __dsqrt_rn(r2));                                              // :147
             const double inv_r3 = __ddiv_rn(inv_r, r2);                                                       // :148
@@ -415,14 +417,15 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             const int plane = n * stride;
             Ti[0] = __dmul_rn(si, dx); Ti[plane] = __dmul_rn(si, dy); Ti[2 * plane] = __dmul_rn(si, dz);
             Tj[0] = -__dmul_rn(sj, dx); Tj[plane] = -__dmul_rn(sj, dy); Tj[2 * plane] = -__dmul_rn(sj, dz);
-            if (DETECT) {
-                if (overlap_exact(-dx, -dy, -dz, sr[i], sr[j])) {    // physics.py:517-518 (ri - rj)
-                    record_overlap(ctl, pairs, i, j);
-                    hit = 1;
-                }
+            if (touching) {
+                record_overlap(ctl, pairs, i, j);
+                hitflag[s & 1] = 1;
             }
         }
-        const int hits = DETECT ? __syncthreads_or(hit) : (__syncthreads(), 0);
+        __syncthreads();
+        // two flags, alternating by step: the one of the next step is cleared while nobody can be setting it
+        const int hits = DETECT ? hitflag[s & 1] : 0;
+        if (DETECT && tid == 0) hitflag[(s + 1) & 1] = 0;
         if (active) {
             const double* row = T + tid * stride;
             const int plane = n * stride;
