@@ -73,10 +73,18 @@ int orb_fp64_peak(int device, double seconds, double* tflops_best, double* tflop
  * (core/engine.py:19-46, core/physics.py:161-191,452-508).
  * orb_create:         all n bodies are integrated on `device`.
  * orb_create_sharded: bodies [tgt_lo, tgt_hi) are integrated here, all n act as
- *                     sources (multi-GPU target partition).     */
+ *                     sources (multi-GPU target partition). Equal
+ *                     slabs imply (rank, world) = (tgt_lo / slab, n / slab).
+ * orb_create_ranked:  the same with an explicit rank / world, for slabs of
+ *                     ceil(n / world) bodies whose last one is shorter. The packed
+ *                     position buffer (orb_pos4_ptr) then holds world * ceil(n / world)
+ *                     entries so that equal-size in-place all-gathers fit; entries
+ *                     >= n are padding no kernel reads.                          */
 int orb_create(orb_engine** out, int64_t n, int device, int mode);
 int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi,
                        int device, int mode);
+int orb_create_ranked(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi,
+                      int rank, int world, int device, int mode);
 int orb_destroy(orb_engine* e);
 
 /* SimulationEngine(dt=, softening=) + STANDARD.G (core/engine.py:31-32, core/constants.py:49-58). */
@@ -123,17 +131,41 @@ int orb_accel(orb_engine* e);
  * contacts with the reference's sequential semantics (core/physics.py:391-422),
  * re-uploads, calls orb_history_append and resumes. Synchronous on return. */
 int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_overlaps);
-/* Overlapping pairs (i<j) of the halted step, unsorted; *count may exceed cap
- * (then only cap pairs were stored and the caller must sweep all pairs). */
+/* Overlapping pairs (i<j) of the halted step (or, on a sharded handle, of the last orb_step_force), unsorted;
+ * *count may exceed the pairs returned (then the list overflowed and the caller must sweep all pairs). */
 int orb_overlap_pairs(orb_engine* e, int64_t* pairs_ij, int64_t cap, int64_t* count);
-/* Split step for sharded engines: begin = half-kick + drift of the local
- * targets (engine.py:69-75); the caller all-gathers orb_pos4_ptr() slabs;
- * finish = force + half-kick (engine.py:78-82). Asynchronous. */
+/* Split step for sharded engines (one handle per rank; core/engine.py:65-97 per step):
+ *   orb_step_begin   half-kick + drift of the local targets (engine.py:69-75)
+ *   [caller]         all-gather the orb_pos4_ptr() slabs across ranks
+ *   orb_step_force   force pass (engine.py:78) with the overlap test of engine.py:85 ->
+ *                    physics.py:517-518 fused in: fills this rank's pair list
+ *   [caller]         all-reduce orb_acc_ptr() if orb_acc_needs_allreduce()
+ *   orb_step_kick    second half-kick of the local targets (engine.py:81-82)
+ *   [caller]         only when some rank reports pairs (orb_overlap_count): all-gather the
+ *                    velocities and the pair lists, orb_set_overlap_pairs(merged list)
+ *   orb_step_end     contact sweep (physics.py:510-535, 391-422) replicated on every rank over
+ *                    the identical full state -- sequential, lexicographic, bit-identical
+ *                    everywhere, each rank keeps its slab -- then the history append of all n
+ *                    bodies (engine.py:88-92) and the step bookkeeping.
+ * orb_step_finish = orb_step_force + orb_step_kick for engines whose accelerations are complete.
+ * On an UNSHARDED handle orb_step_begin / orb_accel / orb_step_kick is a whole step (orb_step_kick then
+ * also appends the history point and advances), which lets a caller bracket the force pass with its own
+ * CUDA events. All asynchronous except orb_overlap_count / orb_set_overlap_pairs. */
 int orb_step_begin(orb_engine* e);
+int orb_step_force(orb_engine* e);
 int orb_step_finish(orb_engine* e);
-/* The second half of orb_step_finish on its own: half-kick (engine.py:81-82) + history append,
- * so a caller can bracket the force pass (orb_accel) with its own CUDA events. */
 int orb_step_kick(orb_engine* e);
+int orb_step_end(orb_engine* e);
+/* Pairs this handle's last force pass flagged (clamped to the list capacity); *overflowed != 0 if some were
+ * dropped. Synchronous. */
+int orb_overlap_count(orb_engine* e, int64_t* count, int* overflowed);
+/* Replace the handle's pair list (e.g. with the union over ranks). overflowed != 0: the list is incomplete, the
+ * sweep of orb_step_end scans all pairs instead (exact, slower). */
+int orb_set_overlap_pairs(orb_engine* e, const int64_t* pairs_ij, int64_t count, int overflowed);
+/* Touching pairs resolved on the device since the last orb_step began / in this handle's life (sharded), and how
+ * many sweeps had to abandon the pair list (more than ORBITAL_B200_OVERLAP_CAP pairs, default 2^20) and scan all
+ * pairs. */
+int orb_contact_stats(orb_engine* e, int64_t* contacts_total, int64_t* full_sweeps);
 /* *flag != 0: on this (sharded, fast-mode) engine orb_accel leaves a PARTIAL acceleration of all n bodies
  * (the pair-symmetric kernel evaluates a cyclic share of the pair blocks per rank); the caller must
  * all-reduce (sum) the 3 x n buffer at orb_acc_ptr across ranks before orb_step_kick. orb_step_finish is
@@ -167,7 +199,8 @@ int orb_history_append(orb_engine* e);
 int orb_history_download(orb_engine* e, int64_t last_k, double* out, int64_t* got);
 
 /* ---- batched ensemble: nsys independent systems of nbody bodies ---------
- * One CTA per system (BASELINE config C3). Arrays are [nsys][nbody] fp64.
+ * BASELINE config C3. Bit-exact mode: one warp per system; fast mode: nbody/2 lanes
+ * per system, 64/nbody systems per warp. Arrays are [nsys][nbody] fp64.
  * Equivalent to nsys separate SimulationEngine instances stepped in lockstep
  * (core/engine.py:19-46,65-97) without collision handling. */
 int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int mode, int vel_f32);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "orb_fp64_peak": (C.c_int, [C.c_int, C.c_double, _dblp, _dblp, _dblp]),
     "orb_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int, C.c_int]),
     "orb_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "orb_create_ranked": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "orb_destroy": (C.c_int, [_vp]),
     "orb_set_params": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
     "orb_set_mode": (C.c_int, [_vp, C.c_int]),
@@ -62,7 +63,12 @@ SIGNATURES = {
     "orb_step": (C.c_int, [_vp, C.c_int64, _i64p, _i64p]),
     "orb_overlap_pairs": (C.c_int, [_vp, _i64, C.c_int64, _i64p]),
     "orb_step_begin": (C.c_int, [_vp]),
+    "orb_step_force": (C.c_int, [_vp]),
     "orb_step_finish": (C.c_int, [_vp]),
+    "orb_step_end": (C.c_int, [_vp]),
+    "orb_overlap_count": (C.c_int, [_vp, _i64p, _intp]),
+    "orb_set_overlap_pairs": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
+    "orb_contact_stats": (C.c_int, [_vp, _i64p, _i64p]),
     "orb_step_kick": (C.c_int, [_vp]),
     "orb_acc_needs_allreduce": (C.c_int, [_vp, _intp]),
     "orb_synchronize": (C.c_int, [_vp]),
@@ -192,15 +198,20 @@ class DeviceSystem:
     """
 
     def __init__(self, n: int, device: int = 0, mode: int = MODE_FAITHFUL, tgt_lo: int | None = None,
-                 tgt_hi: int | None = None):
+                 tgt_hi: int | None = None, rank: int | None = None, world: int | None = None):
         self._h = _vp()
         self.n = int(n)
         self.device = int(device)
         self.mode = int(mode)
         self.tgt_lo = 0 if tgt_lo is None else int(tgt_lo)
         self.tgt_hi = self.n if tgt_hi is None else int(tgt_hi)
+        self.pos4_capacity = self.n
         L = lib()
-        if self.tgt_lo == 0 and self.tgt_hi == self.n:
+        if world is not None:
+            check(L.orb_create_ranked(C.byref(self._h), self.n, self.tgt_lo, self.tgt_hi, int(rank or 0), int(world),
+                                      self.device, self.mode))
+            self.pos4_capacity = max(self.n, int(world) * -(-self.n // int(world)))
+        elif self.tgt_lo == 0 and self.tgt_hi == self.n:
             check(L.orb_create(C.byref(self._h), self.n, self.device, self.mode))
         else:
             check(L.orb_create_sharded(C.byref(self._h), self.n, self.tgt_lo, self.tgt_hi, self.device, self.mode))
@@ -287,8 +298,30 @@ class DeviceSystem:
     def step_begin(self):
         check(lib().orb_step_begin(self._h))
 
+    def step_force(self):
+        check(lib().orb_step_force(self._h))
+
     def step_finish(self):
         check(lib().orb_step_finish(self._h))
+
+    def step_end(self):
+        check(lib().orb_step_end(self._h))
+
+    def overlap_count(self):
+        """-> (pairs flagged by the last force pass, list overflowed?)  Synchronises."""
+        c, o = C.c_int64(0), C.c_int(0)
+        check(lib().orb_overlap_count(self._h, C.byref(c), C.byref(o)))
+        return c.value, bool(o.value)
+
+    def set_overlap_pairs(self, pairs, overflowed: bool = False):
+        p = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        check(lib().orb_set_overlap_pairs(self._h, p.ctypes.data_as(_vp) if len(p) else None, len(p),
+                                          int(bool(overflowed))))
+
+    def contact_stats(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(lib().orb_contact_stats(self._h, C.byref(a), C.byref(b)))
+        return {"contacts_total": a.value, "full_sweeps": b.value}
 
     def step_kick(self):
         check(lib().orb_step_kick(self._h))

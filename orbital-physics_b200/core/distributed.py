@@ -1,22 +1,36 @@
-"""Multi-GPU large-N run: target bodies partitioned by rank, positions all-gathered each step.
+"""Multi-GPU large-N run: bodies partitioned over ranks, positions all-gathered each step.
 
-One process per GPU (torch.distributed, NCCL over NVLink); SURVEY.md 8(e).
-Every rank holds all N sources {x,y,z,m} (32 B per body) and integrates the
-contiguous target slab [lo, hi).  Per step:
+SURVEY.md 8(e).  Every rank holds all N sources {x,y,z,m} (32 B per body) and integrates a contiguous
+slab of ceil(N / world) bodies.  One leapfrog step (reference core/engine.py:65-97) is
 
-    orb_step_begin   half-kick + drift of the local slab           (rank-local)
-    all_gather       the packed {x,y,z,m} slabs, in place           (NCCL, 32*N bytes total)
-    orb_accel        force pass                                     (rank-local)
-    [all_reduce      3 x N accelerations, fast mode only]           (NCCL, 24*N bytes)
-    orb_step_kick    half-kick of the local slab                    (rank-local)
+    orb_step_begin   half-kick + drift of the local slab                       (rank-local)
+    all_gather       the packed {x,y,z,m} slabs, in place                      (32 B x N in total)
+    orb_step_force   force pass with the overlap test of engine.py:85 fused in (rank-local)
+    [all_reduce      3 x N accelerations, pair-symmetric fast kernel only]     (24 B x N)
+    orb_step_kick    second half-kick of the local slab                        (rank-local)
+    [contacts        only in a step where some rank flagged a pair: all-gather the velocities and the pair
+                     lists; every rank then replays the reference's sequential sweep (physics.py:510-535)
+                     over the identical full state -- bit-identical everywhere, each rank keeps its slab]
+    orb_step_end     history append (all N bodies) + bookkeeping               (rank-local)
 
-Faithful mode: every rank evaluates its own targets against all sources; each
-target's source order is unchanged by the partition, so the result is
-bit-identical to the single-GPU run.  Fast mode: the pair-symmetric kernel
-evaluates every unordered pair once, so each rank takes a cyclic share of the
-pair blocks and produces a partial acceleration of all N bodies, summed by one
-all-reduce.  The reference has no distributed path; the
-per-step semantics are the reference's core/engine.py:65-97.
+Bit-exact mode: every rank evaluates its own targets against all sources; a target's source order does
+not depend on the partition, so the result is bit-identical to one GPU.  Fast mode: the pair-symmetric
+kernel evaluates every unordered pair once, so each rank takes a cyclic share of the pair blocks and
+produces a partial acceleration of all N bodies, summed by the all-reduce.
+
+Two communicators carry the same protocol:
+
+* :class:`DistComm`  -- production: one process per GPU, ``torch.distributed`` (NCCL over NVLink; gloo in
+  the CPU tests).  Every process constructs the same :class:`ShardedSystem` / ``SimulationEngine`` and makes
+  the same calls in the same order (SPMD).
+* :class:`LocalComm` -- all ranks live in this process, one handle per listed device; peers exchange slabs
+  with device-to-device copies.  Listing one device several times (``devices=[0, 0]``) runs the real
+  per-rank kernels of a multi-GPU job on a single GPU, which is how the sharded kernels are held to the
+  oracle on a one-GPU box (tests/test_sharded_gpu.py).
+
+:class:`ShardedSystem` has the interface of ``core._native.DeviceSystem``, so ``SimulationEngine`` drives
+either (``SimulationEngine(..., devices=...)``): run(), history, diagnostics and JSONL frames are unchanged.
+The reference has no distributed path; the per-step semantics are the reference's.
 """
 from __future__ import annotations
 
@@ -26,11 +40,12 @@ from core import _native
 
 
 def slab(n: int, world_size: int, rank: int):
-    """Equal contiguous target slabs (n must be divisible by world_size: pad with massless bodies otherwise)."""
-    if n % world_size:
-        raise ValueError(f"n={n} must be divisible by world_size={world_size}")
-    per = n // world_size
-    return rank * per, (rank + 1) * per
+    """Contiguous slab of ceil(n / world_size) bodies; the last ranks' slabs may be shorter (never empty)."""
+    per = -(-n // world_size)
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+    if lo >= hi:
+        raise ValueError(f"n={n} bodies leave rank {rank} of {world_size} without a slab: use fewer ranks")
+    return lo, hi
 
 
 class _CudaView:
@@ -41,84 +56,319 @@ class _CudaView:
                                          "version": 3, "strides": None}
 
 
-class ShardedSystem:
-    """N bodies over `world_size` ranks. All ranks pass the same full initial condition."""
+# --------------------------------------------------------------------------- communicators
+class DistComm:
+    """One process per GPU over torch.distributed: this process holds exactly one rank."""
 
-    def __init__(self, x, y, z, vx, vy, vz, m, radius, dt, eps, G=6.67430e-11, mode=_native.MODE_FAST,
-                 group=None, device=None, vel_is_f32=None):
+    def __init__(self, group=None, device=None):
         import torch
         import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("DistComm needs torch.distributed.init_process_group() first")
         self.torch, self.dist, self.group = torch, dist, group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.n = int(np.asarray(x).shape[0])
-        self.lo, self.hi = slab(self.n, self.world, self.rank)
-        self.device = self.rank % max(1, _native.device_count()) if device is None else int(device)
-        self.dev = self._make_device(mode)
-        self.dev.set_params(dt, eps, G)
-        self.dev.upload(x, y, z, vx, vy, vz, m, radius, vel_is_f32)
-        self._pos4 = self._view("pos4", (self.n, 4))
-        self._vel = self._view("vel", (3, self.n))
-        self._acc = self._view("acc", (3, self.n))
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.local_ranks = [self.rank]
+        if device is None:
+            device = self.rank % max(1, _native.device_count())
+        self.devices = {self.rank: int(device)}
+
+    def all_gather_rows(self, bufs, per):
+        """bufs[0]: [world * per, ...] tensor whose rows [rank*per, (rank+1)*per) are this rank's; in place."""
+        flat = bufs[0].view(-1)
+        k = flat.numel() // self.world
+        self.dist.all_gather_into_tensor(flat, flat[self.rank * k:(self.rank + 1) * k], group=self.group)
+
+    def all_reduce_sum(self, bufs):
+        self.dist.all_reduce(bufs[0], group=self.group)
+
+    def all_gather_host(self, items):
+        """items[0]: any picklable object of this rank -> list over ranks."""
+        out = [None] * self.world
+        self.dist.all_gather_object(out, items[0], group=self.group)
+        return out
+
+
+class LocalComm:
+    """All ranks in this process, rank r on devices[r] (a device may carry several ranks)."""
+
+    def __init__(self, devices):
+        import torch
+        self.torch = torch
+        devices = [int(d) for d in devices]
+        self.world = len(devices)
+        self.local_ranks = list(range(self.world))
+        self.devices = dict(enumerate(devices))
+        self.rank = 0
+
+    def all_gather_rows(self, bufs, per):
+        n_rows = bufs[0].shape[0]
+        for r, src in enumerate(bufs):
+            lo, hi = r * per, min(n_rows, (r + 1) * per)
+            for q, dst in enumerate(bufs):
+                if q != r:
+                    dst[lo:hi].copy_(src[lo:hi], non_blocking=True)
+
+    def all_reduce_sum(self, bufs):
+        total = bufs[0].clone()
+        for b in bufs[1:]:                      # fixed rank order: deterministic
+            total += b.to(total.device, non_blocking=True)
+        for b in bufs:
+            b.copy_(total, non_blocking=True)
+
+    def all_gather_host(self, items):
+        return list(items)
+
+
+# --------------------------------------------------------------------------- the sharded system
+class ShardedSystem:
+    """N bodies over `comm.world` ranks behind the interface of ``core._native.DeviceSystem``.
+
+    All ranks pass the same full arrays to :meth:`upload`.  `step(k)` returns `(k, contacts resolved)` like a
+    handle with device-side contact resolution -- sharded engines always resolve contacts on the device.
+    """
+
+    def __init__(self, n: int, mode: int = _native.MODE_FAST, comm=None):
+        self.comm = comm if comm is not None else DistComm()
+        self.torch = self.comm.torch
+        self.n, self.mode = int(n), int(mode)
+        self.world, self.rank = self.comm.world, self.comm.rank
+        self.per = -(-self.n // self.world)
+        self.slabs = [slab(self.n, self.world, r) for r in range(self.world)]     # raises if a rank would be empty
+        self.lo, self.hi = self.slabs[self.rank]
+        self.devs, self._pos4, self._vel, self._acc = [], [], [], []
+        for r in self.comm.local_ranks:
+            lo, hi = self.slabs[r]
+            dev = self._make_device(r, lo, hi)
+            self.devs.append(dev)
+            self._pos4.append(self._view(dev, "pos4", (self.world * self.per, 4)))
+            self._vel.append(self._view(dev, "vel", (3, self.n)))
+            self._acc.append(self._view(dev, "acc", (3, self.n)))
+            self._bind_stream(dev)
+        self.dev = self.devs[0]
         self._partial = bool(self.dev.acc_needs_allreduce()) and self.world > 1
-        self._bind_stream()
-        self._force()                         # engine.py:41
+        self._detect = False
+        self._acc_full = True
         self.steps_done = 0
+        self.comm_events = None        # set to a list to collect (start, end) CUDA events around the collectives
+
+    @classmethod
+    def from_arrays(cls, x, y, z, vx, vy, vz, m, radius, dt, eps, G=6.67430e-11, mode=_native.MODE_FAST,
+                    comm=None, vel_is_f32=None, restitution=1.0):
+        """Construct, configure, upload and run the constructor force pass (engine.py:41)."""
+        s = cls(int(np.asarray(x).shape[0]), mode, comm)
+        s.set_params(dt, eps, G)
+        s.set_contacts(restitution, True)
+        s.upload(x, y, z, vx, vy, vz, m, radius, vel_is_f32)
+        s.accel()
+        return s
 
     # -- backend seams (overridden by the CPU test double) ------------------
-    def _make_device(self, mode):
-        return _native.DeviceSystem(self.n, self.device, mode, self.lo, self.hi)
+    def _make_device(self, rank, lo, hi):
+        return _native.DeviceSystem(self.n, self.comm.devices[rank], self.mode, lo, hi, rank=rank, world=self.world)
 
-    def _view(self, which, shape):
-        ptr = {"pos4": self.dev.pos4_ptr, "vel": self.dev.vel_ptr, "acc": self.dev.acc_ptr}[which]()
-        return self.torch.as_tensor(_CudaView(ptr, shape), device=f"cuda:{self.device}")
+    def _view(self, dev, which, shape):
+        ptr = {"pos4": dev.pos4_ptr, "vel": dev.vel_ptr, "acc": dev.acc_ptr}[which]()
+        return self.torch.as_tensor(_CudaView(ptr, shape), device=f"cuda:{dev.device}")
 
-    def _bind_stream(self):
-        self.torch.cuda.set_device(self.device)
-        self.dev.set_stream(self.torch.cuda.current_stream().cuda_stream)
+    def _bind_stream(self, dev):
+        # the library runs on torch's current stream of the handle's device, so torch's stream semantics order
+        # its kernels with the collectives / peer copies
+        dev.set_stream(self.torch.cuda.current_stream(dev.device).cuda_stream)
 
-    # -- stepping -----------------------------------------------------------
-    def _all_gather_positions(self):
+    # -- configuration ------------------------------------------------------
+    def set_params(self, dt, eps, G=6.67430e-11):
+        for d in self.devs:
+            d.set_params(dt, eps, G)
+
+    def set_mode(self, mode):
+        for d in self.devs:
+            d.set_mode(mode)
+        self.mode = int(mode)
+        self._partial = bool(self.dev.acc_needs_allreduce()) and self.world > 1
+
+    def set_contacts(self, restitution, on_device=True):
+        if not on_device:
+            raise ValueError("sharded engines resolve contacts on the device (contacts='device')")
+        for d in self.devs:
+            d.set_contacts(restitution, True)
+
+    def set_history(self, capacity):
+        # every process keeps the full ring (any rank's engine may be asked for it); in-process ranks share one
+        for k, d in enumerate(self.devs):
+            d.set_history(capacity if k == 0 else 0)
+
+    def set_stream(self, cuda_stream):
+        for d in self.devs:
+            d.set_stream(cuda_stream)
+
+    # -- transfers ----------------------------------------------------------
+    def upload(self, x, y, z, vx, vy, vz, m, radius, vel_is_f32=None):
+        for d in self.devs:
+            d.upload(x, y, z, vx, vy, vz, m, radius, vel_is_f32)
+        self._detect = bool(np.any(np.asarray(radius) > 0.0))
+
+    def _gather_rows3(self, views):
+        """Make rows [3, n] complete on every rank from the per-rank slabs (velocities, accelerations)."""
         if self.world == 1:
             return
-        flat = self._pos4.view(-1)
-        per = (self.hi - self.lo) * 4
-        self.dist.all_gather_into_tensor(flat, flat[self.lo * 4: self.lo * 4 + per], group=self.group)
+        if isinstance(self.comm, LocalComm):
+            for r, src in enumerate(views):
+                lo, hi = self.slabs[r]
+                for q, dst in enumerate(views):
+                    if q != r:
+                        dst[:, lo:hi].copy_(src[:, lo:hi], non_blocking=True)
+            return
+        t = self.torch
+        v = views[0]
+        tmp = t.zeros((self.world * self.per,), dtype=v.dtype, device=v.device)
+        for c in range(3):
+            piece = tmp[self.rank * self.per:(self.rank + 1) * self.per]
+            piece[: self.hi - self.lo].copy_(v[c, self.lo:self.hi])
+            self.comm.all_gather_rows([tmp], self.per)
+            v[c].copy_(tmp[: self.n])
 
-    def _force(self):
-        self.dev.accel()
+    def download_state(self, out=None):
+        """Full x y z vx vy vz (positions are complete on every rank; velocities are gathered first)."""
+        self._gather_rows3(self._vel)
+        return self.dev.download_state(out)
+
+    def download_acc(self):
+        if not self._acc_full:
+            self._gather_rows3(self._acc)
+            self._acc_full = True
+        return self.dev.download_acc()
+
+    def upload_acc(self, acc3n):
+        for d in self.devs:
+            d.upload_acc(acc3n)
+        self._acc_full = True
+
+    # -- stepping -----------------------------------------------------------
+    def _timed(self, fn):
+        if self.comm_events is None:
+            return fn()
+        ev = self.torch.cuda.Event
+        a, b = ev(enable_timing=True), ev(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        self.comm_events.append((a, b))
+
+    def _all_gather_positions(self):
+        if self.world > 1:
+            self._timed(lambda: self.comm.all_gather_rows(self._pos4, self.per))
+
+    def _reduce_acc(self):
         if self._partial:
-            self.dist.all_reduce(self._acc, group=self.group)
+            self._timed(lambda: self.comm.all_reduce_sum(self._acc))
+        self._acc_full = self._partial or self.world == 1
+
+    def accel(self):
+        """Constructor force pass (engine.py:41): no overlap test."""
+        for d in self.devs:
+            d.accel()
+        self._reduce_acc()
+
+    def _contacts(self) -> int:
+        """engine.py:85 across ranks. Returns the number of candidate pairs handed to the sweep (0: none)."""
+        local = [d.overlap_count() for d in self.devs]              # synchronises each local handle
+        every = self.comm.all_gather_host(local)
+        total = sum(c for c, _ in every)
+        overflow = any(o for _, o in every)
+        if total == 0 and not overflow:
+            return 0
+        self._gather_rows3(self._vel)                               # the sweep needs every body's velocity
+        mine = [d.overlap_pairs(cap=max(1, c))[0] for d, (c, _) in zip(self.devs, local)]
+        lists = self.comm.all_gather_host(mine)
+        merged = np.concatenate([np.asarray(p, dtype=np.int64).reshape(-1, 2) for p in lists], axis=0)
+        for d in self.devs:
+            d.set_overlap_pairs(merged, overflow)
+        return max(1, len(merged))
 
     def step(self, nsteps: int = 1):
+        before = self.dev.contact_stats()["contacts_total"] if self._detect else 0
         for _ in range(int(nsteps)):
-            self.dev.step_begin()
+            for d in self.devs:
+                d.step_begin()
             self._all_gather_positions()
-            self._force()
-            self.dev.step_kick()
+            for d in self.devs:
+                d.step_force()
+            self._reduce_acc()
+            for d in self.devs:
+                d.step_kick()
+            if self._detect:
+                self._contacts()
+            for d in self.devs:
+                d.step_end()
         self.steps_done += int(nsteps)
+        resolved = self.dev.contact_stats()["contacts_total"] - before if self._detect else 0
+        return int(nsteps), int(resolved)
 
     def synchronize(self):
-        self.dev.synchronize()
+        for d in self.devs:
+            d.synchronize()
 
     # -- results ------------------------------------------------------------
     def gather_state(self) -> dict:
-        """Full x y z vx vy vz on every rank (velocities are all-gathered: each rank owns its slab)."""
-        if self.world > 1:
-            per = self.hi - self.lo
-            for c in range(3):
-                row = self._vel[c]
-                self.dist.all_gather_into_tensor(row, row[self.lo: self.lo + per].clone(), group=self.group)
-        return self.dev.download_state()
+        return self.download_state()
+
+    def overlap_pairs(self, cap: int = 1 << 16):
+        raise RuntimeError("sharded engines resolve contacts on the device; there is no halted pair list")
+
+    def potential(self) -> float:
+        """U of the resident positions: they are complete on every rank, so each evaluates it alone."""
+        return self.dev.potential()
 
     def energy_angmom(self):
-        """(K, L[3]) summed over ranks (engine.py:104-121)."""
-        K, L = self.dev.energy_angmom()
-        if self.world > 1:
-            t = self.torch.tensor([K, L[0], L[1], L[2]], dtype=self.torch.float64, device=self._pos4.device)
-            self.dist.all_reduce(t, group=self.group)
-            K, L = float(t[0]), t[1:].cpu().numpy()
-        return K, L
+        """(K, L[3]) summed over ranks in rank order (engine.py:104-121)."""
+        parts = [d.energy_angmom() for d in self.devs]
+        local = [np.concatenate([[k], L]) for k, L in parts]
+        every = self.comm.all_gather_host(local)
+        tot = np.zeros(4)
+        for p in every:
+            tot += p
+        return float(tot[0]), tot[1:].copy()
+
+    def history_count(self):
+        return self.dev.history_count()
+
+    def history_append(self):
+        for d in self.devs:
+            d.history_append()
+
+    def history_download(self, last_k):
+        return self.dev.history_download(last_k)
+
+    def force_kernel_info(self) -> dict:
+        info = dict(self.dev.force_kernel_info())
+        info["world"] = self.world
+        return info
+
+    def launch_count(self) -> int:
+        return sum(d.launch_count() for d in self.devs)
+
+    def contact_stats(self):
+        return self.dev.contact_stats()
+
+    def acc_needs_allreduce(self):
+        return self._partial
 
     def close(self):
-        self.dev.close()
+        for d in self.devs:
+            d.close()
+        self.devs = []
+
+
+def make_comm(devices):
+    """`devices` of SimulationEngine(..., devices=...): "dist" -> DistComm (torch.distributed must be initialised);
+    an int N -> LocalComm over GPUs 0..N-1; a list -> LocalComm with one rank per entry."""
+    if isinstance(devices, str):
+        if devices.lower() != "dist":
+            if devices.isdigit():
+                return make_comm(int(devices))
+            return make_comm([int(t) for t in devices.split(",") if t.strip()])
+        return DistComm()
+    if isinstance(devices, int):
+        return LocalComm(range(devices))
+    return LocalComm(devices)

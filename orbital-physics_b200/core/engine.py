@@ -11,8 +11,13 @@ methods; `run_simulation` prints the same diagnostics).  The state of the bound
 and `run(k)` keeps all k steps on the device (CUDA graph / fused single-CTA
 kernel).  The Python `Object`s are lazy mirrors: the first read after a step
 pulls the state once; a write makes the host copy authoritative and it is
-re-uploaded before the next step.  Contacts are detected on the device and
-resolved on the host with the reference's sequential semantics.
+re-uploaded before the next step.  Contacts are detected in the force pass and
+resolved with the reference's sequential semantics -- on the device by default
+(`contacts="device"`), or by the host replay (`contacts="host"`).
+
+`devices=` spreads one system over several GPUs (core/distributed.py): the
+same engine object, `run()`, `history`, diagnostics and JSONL frames on top of
+a `ShardedSystem` instead of a single `DeviceSystem`.
 
 Reference behaviour kept on purpose: `max_hist=-1` keeps only the
 latest history point; `cache=True` by default appends a JSONL frame every
@@ -77,12 +82,16 @@ class SimulationEngine:
         device:   CUDA device index             (env ORBITAL_B200_DEVICE / LOCAL_RANK)
         contacts: "device" | "host"             (env ORBITAL_B200_CONTACTS) -- where overlapping pairs are
                   resolved; both replay the reference's sequential sweep exactly. "device" never leaves the GPU.
+        devices:  None | N | [d0, d1, ...] | "dist"  (env ORBITAL_B200_DEVICES) -- multi-GPU: N GPUs driven by this
+                  process, an explicit device per rank, or "dist" = one process per GPU under torchrun
+                  (torch.distributed already initialised; every rank builds the same engine and makes the
+                  same calls).  Bit-exact mode stays bit-identical to one GPU.  Needs contacts="device".
     """
 
     def __init__(self, objects: ObjectCollection, dt: float = 1.0, softening: float = 0.0,
                  restitution: float = 1.0, max_hist: int = -1, cache: bool = True,
                  cache_fp: str = "history.jsonl", cache_every_n: int = 300, *, mode=None, device=None,
-                 contacts=None):
+                 contacts=None, devices=None):
         self._lock = threading.RLock()
         self.objects = objects
         self.dt = float(dt)
@@ -98,6 +107,10 @@ class SimulationEngine:
         if self._contacts not in ("device", "host"):
             raise ValueError("contacts must be 'device' or 'host'")
         self._device = default_device() if device is None else int(device)
+        self._devices = devices if devices is not None else (os.environ.get("ORBITAL_B200_DEVICES") or None)
+        self._comm = None
+        if self._devices is not None and self._contacts != "device":
+            raise ValueError("a multi-GPU engine resolves contacts on the device: use contacts='device'")
         self._G = STANDARD.G       # the reference never forwards unit_profile (engine.py:41,78)
 
         self._dev = None
@@ -187,7 +200,7 @@ class SimulationEngine:
             self._acc_cache = (self._force_version, {})
             self._U_cache = (self._force_version, 0.0)
             return
-        self._dev = _native.DeviceSystem(n, self._device, select_mode(n, self._mode_req))
+        self._dev = self._new_device(n, select_mode(n, self._mode_req))
         self._sync_params()
         limit = self._hist_limit()
         per_snapshot = 24 * n
@@ -208,6 +221,16 @@ class SimulationEngine:
             a = np.array([old_acc[u] for u in self._uuids]).T   # KeyError for late-added bodies, as the reference
             self._dev.upload_acc(np.ascontiguousarray(a))
             self._acc_cache = (self._force_version, {u: old_acc[u] for u in self._uuids})
+
+    def _new_device(self, n, mode):
+        if self._devices is None:
+            return _native.DeviceSystem(n, self._device, mode)
+        from core import distributed
+        if self._comm is None:
+            self._comm = distributed.make_comm(self._devices)
+        if self._comm.world == 1:
+            return _native.DeviceSystem(n, next(iter(self._comm.devices.values())), mode)
+        return distributed.ShardedSystem(n, mode, self._comm)
 
     # ------------------------------------------------------------ lazy mirroring
     def _host_read(self):

@@ -60,6 +60,8 @@ struct orb_engine {
     int mode = ORB_MODE_FAITHFUL;
     int sm_count = 148;
     bool sharded = false;
+    int rank = 0, world = 1;         // pair-block ownership of the pair-symmetric kernel (world 0: not available)
+    long long pos4_cap = 0;          // entries allocated for pos4 (>= n: padded so equal-size all-gathers fit)
     DeviceState s;
     StepParams p{};
     FastPlan plan;
@@ -94,15 +96,8 @@ bool use_tiny(const orb_engine* e) {
     return e->mode == ORB_MODE_FAITHFUL && !e->sharded && e->s.n <= tiny_limit();
 }
 
-// world / rank of a sharded engine with equal slabs (0 when the slabs are not equal)
-int shard_world(const orb_engine* e) {
-    const long long per = e->s.tgt_hi - e->s.tgt_lo;
-    if (per <= 0 || e->s.n % per || e->s.tgt_lo % per) return 0;
-    return (int)(e->s.n / per);
-}
-
 bool sym_applicable(const orb_engine* e) {
-    return e->mode == ORB_MODE_FAST && e->use_sym && (!e->sharded || shard_world(e) > 0);
+    return e->mode == ORB_MODE_FAST && e->use_sym && (!e->sharded || e->world > 0);
 }
 
 // pair-symmetric force on a sharded engine: every rank evaluates a cyclic share of the I-blocks and
@@ -132,9 +127,7 @@ int ensure_plan(orb_engine* e) {
     }
     if (sym_applicable(e)) {
         if (!e->sym.valid) {
-            const int world = e->sharded ? shard_world(e) : 1;
-            const int rank = e->sharded ? (int)(e->s.tgt_lo / (e->s.tgt_hi - e->s.tgt_lo)) : 0;
-            CU(plan_sym(e->sym, e->s.n, e->sm_count, rank, world));
+            CU(plan_sym(e->sym, e->s.n, e->sm_count, e->sharded ? e->rank : 0, e->sharded ? e->world : 1));
         }
         return ORB_OK;
     }
@@ -224,13 +217,19 @@ int build_graph(orb_engine* e, int steps, cudaGraphExec_t* out) {
 
 int alloc_engine(orb_engine* e) {
     const long long n = e->s.n;
-    CU(cudaMalloc(&e->s.pos4, sizeof(double4) * n));
+    CU(cudaMalloc(&e->s.pos4, sizeof(double4) * std::max(n, e->pos4_cap)));
+    CU(cudaMemset(e->s.pos4, 0, sizeof(double4) * std::max(n, e->pos4_cap)));
     CU(cudaMalloc(&e->s.vel, sizeof(double) * 3 * n));
     CU(cudaMalloc(&e->s.acc, sizeof(double) * 3 * n));
     CU(cudaMalloc(&e->s.radius, sizeof(double) * n));
     CU(cudaMalloc(&e->s.vf32, n));
     CU(cudaMalloc(&e->s.ctl, sizeof(Ctl)));
-    CU(cudaMalloc(&e->s.pairs, sizeof(long long) * 2 * kOverlapCap));
+    {
+        const char* env = getenv("ORBITAL_B200_OVERLAP_CAP");
+        const long long v = env ? atoll(env) : (long long)kOverlapCapDefault;
+        e->s.pairs_cap = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 28));
+    }
+    CU(cudaMalloc(&e->s.pairs, sizeof(long long) * 2 * e->s.pairs_cap));
     CU(cudaMalloc(&e->s.reduce_buf, sizeof(double) * 4 * ((n + 255) / 256 + 1)));
     CU(cudaMalloc(&e->d_stage, sizeof(double) * 4 * n));
     CU(cudaMalloc(&e->d_diag, sizeof(double) * 8));
@@ -238,7 +237,12 @@ int alloc_engine(orb_engine* e) {
     CU(cudaMallocHost(&e->h_ctl, sizeof(Ctl)));
     CU(cudaMemset(e->s.vel, 0, sizeof(double) * 3 * n));
     CU(cudaMemset(e->s.acc, 0, sizeof(double) * 3 * n));
-    CU(cudaMemset(e->s.ctl, 0, sizeof(Ctl)));
+    {
+        Ctl init;
+        memset(&init, 0, sizeof init);
+        init.pairs_cap = e->s.pairs_cap;
+        CU(cudaMemcpy(e->s.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice));
+    }
     CU(cudaMemset(e->s.vf32, 0, n));
     CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
@@ -296,7 +300,7 @@ int orb_device_info(int device, char* name, int name_len, int* sm_count, int* cc
                     int64_t* total_mem_bytes) {
     int rc = select_device(device);
     if (rc) return rc;
-    cudaDeviceProp prop;
+    cudaDeviceProp prop{};
     CU(cudaGetDeviceProperties(&prop, device));
     if (name && name_len > 0) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
     if (sm_count) *sm_count = prop.multiProcessorCount;
@@ -328,12 +332,17 @@ int orb_fp64_peak(int device, double seconds, double* tflops_best, double* tflop
     return ORB_OK;
 }
 
-int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi, int device, int mode) {
+}  // extern "C"
+
+namespace {
+int create_engine(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi, int rank, int world, int device,
+                  int mode) {
     if (!out) return fail(ORB_ERR_INVALID, "null out pointer");
     *out = nullptr;
     if (n <= 0) return fail(ORB_ERR_INVALID, "n must be positive");
     if (tgt_lo < 0 || tgt_hi > n || tgt_lo >= tgt_hi) return fail(ORB_ERR_INVALID, "bad target range");
     if (mode != ORB_MODE_FAITHFUL && mode != ORB_MODE_FAST) return fail(ORB_ERR_INVALID, "bad mode");
+    if (world < 0 || (world > 0 && (rank < 0 || rank >= world))) return fail(ORB_ERR_INVALID, "bad rank / world");
     int rc = select_device(device);
     if (rc) return rc;
     orb_engine* e = new orb_engine();
@@ -343,11 +352,15 @@ int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_
     e->s.tgt_lo = tgt_lo;
     e->s.tgt_hi = tgt_hi;
     e->sharded = !(tgt_lo == 0 && tgt_hi == n);
+    e->rank = e->sharded ? rank : 0;
+    e->world = e->sharded ? world : 1;
+    // equal-size in-place all-gathers of the packed positions need world * ceil(n / world) entries
+    e->pos4_cap = world > 0 ? (long long)world * ((n + world - 1) / world) : n;
     {
         const char* env = getenv("ORBITAL_B200_SYM");     // "0": one-sided fast kernel even when unsharded
         e->use_sym = !(env && env[0] == '0');
     }
-    cudaDeviceProp prop;
+    cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) {
         delete e;
@@ -361,9 +374,29 @@ int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_
     *out = e;
     return ORB_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int orb_create_sharded(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi, int device, int mode) {
+    // equal slabs imply (rank, world); anything else cannot use the pair-symmetric kernel (world 0)
+    int rank = 0, world = 0;
+    const int64_t per = tgt_hi - tgt_lo;
+    if (per > 0 && n % per == 0 && tgt_lo % per == 0) {
+        world = (int)(n / per);
+        rank = (int)(tgt_lo / per);
+    }
+    return create_engine(out, n, tgt_lo, tgt_hi, rank, world, device, mode);
+}
+
+int orb_create_ranked(orb_engine** out, int64_t n, int64_t tgt_lo, int64_t tgt_hi, int rank, int world, int device,
+                      int mode) {
+    if (world < 1) return fail(ORB_ERR_INVALID, "world must be >= 1");
+    return create_engine(out, n, tgt_lo, tgt_hi, rank, world, device, mode);
+}
 
 int orb_create(orb_engine** out, int64_t n, int device, int mode) {
-    return orb_create_sharded(out, n, 0, n, device, mode);
+    return create_engine(out, n, 0, n, 0, 1, device, mode);
 }
 
 int orb_destroy(orb_engine* e) {
@@ -391,8 +424,6 @@ int orb_set_params(orb_engine* e, double dt, double eps, double G) {
 
 int orb_set_contacts(orb_engine* e, double restitution, int resolve_on_device) {
     LOCK(e);
-    if (e->sharded && resolve_on_device)
-        return fail(ORB_ERR_INVALID, "device-side contact resolution is not available on sharded engines");
     e->p.restitution = restitution;
     e->p.device_contacts = resolve_on_device ? 1 : 0;
     drop_graphs(e);
@@ -411,7 +442,6 @@ int orb_set_mode(orb_engine* e, int mode) {
 int orb_set_history(orb_engine* e, int64_t capacity) {
     LOCK(e);
     if (capacity < 0) return fail(ORB_ERR_INVALID, "negative capacity");
-    if (e->sharded && capacity > 0) return fail(ORB_ERR_INVALID, "history ring is not available on sharded engines");
     CU(cudaStreamSynchronize(e->stream));
     drop_graphs(e);
     if (e->s.hist) { cudaFree(e->s.hist); e->s.hist = nullptr; }
@@ -553,11 +583,6 @@ int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_over
                 e->launches += launches;
                 if (rc) return rc;
             }
-        } else if (false) {
-            int launches = 0;
-            int rc = enqueue_step(e, &launches);
-            e->launches += launches;
-            if (rc) return rc;
         } else {
             int64_t left = nsteps;
             if (left >= kGraphSteps) {
@@ -592,12 +617,12 @@ int orb_overlap_pairs(orb_engine* e, int64_t* pairs_ij, int64_t cap, int64_t* co
     CU(cudaStreamSynchronize(e->stream));
     const int64_t total = e->h_ctl->overlap_count;
     *count = total;
-    const int64_t stored = std::min<int64_t>(std::min<int64_t>(total, kOverlapCap), cap);
+    const int64_t stored = std::min<int64_t>(std::min<int64_t>(total, e->s.pairs_cap), cap);
     if (pairs_ij && stored > 0) {
         CU(cudaMemcpyAsync(pairs_ij, e->s.pairs, sizeof(long long) * 2 * stored, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
     }
-    if (total > kOverlapCap) *count = total;   // caller sees count > cap -> full sweep
+    // total > the list's capacity: the caller sees count > stored pairs and must sweep all pairs
     return ORB_OK;
 }
 
@@ -621,7 +646,7 @@ int orb_step_finish(orb_engine* e) {
         return fail(ORB_ERR_INVALID, "this sharded engine produces partial accelerations: use orb_accel, all-reduce "
                                      "orb_acc_ptr across ranks, then orb_step_kick");
     int launches = 0;
-    int rc = enqueue_force(e, false, &launches);
+    int rc = enqueue_force(e, e->detect, &launches);     // engine.py:78 + the overlap test of :85 (physics.py:517)
     if (rc) return rc;
     CU(launch_kick_hist(e->s, e->p, e->stream));
     e->launches += launches + 1;
@@ -631,8 +656,61 @@ int orb_step_finish(orb_engine* e) {
 int orb_step_kick(orb_engine* e) {
     LOCK(e);
     CU(launch_kick_hist(e->s, e->p, e->stream));
-    CU(launch_advance(e->s, e->stream));
-    e->launches += 2;
+    ++e->launches;
+    if (!e->sharded) {              // a sharded step is closed by orb_step_end, once all ranks' contacts are known
+        CU(launch_advance(e->s, e->stream));
+        ++e->launches;
+    }
+    return ORB_OK;
+}
+
+int orb_step_force(orb_engine* e) {
+    LOCK(e);
+    if (!e->have_state) return fail(ORB_ERR_INVALID, "orb_step_force before orb_upload");
+    int launches = 0;
+    int rc = enqueue_force(e, e->detect, &launches);
+    e->launches += launches;
+    return rc;
+}
+
+int orb_overlap_count(orb_engine* e, int64_t* count, int* overflowed) {
+    LOCK(e);
+    CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (count) *count = std::min<int64_t>(e->h_ctl->overlap_count, e->s.pairs_cap);
+    if (overflowed) *overflowed = (e->h_ctl->overlap_overflow > 0 || e->h_ctl->overlap_count > e->s.pairs_cap) ? 1 : 0;
+    return ORB_OK;
+}
+
+int orb_set_overlap_pairs(orb_engine* e, const int64_t* pairs_ij, int64_t count, int overflowed) {
+    LOCK(e);
+    if (count < 0 || (count > 0 && !pairs_ij)) return fail(ORB_ERR_INVALID, "bad pair list");
+    if (count > e->s.pairs_cap) { count = e->s.pairs_cap; overflowed = 1; }
+    if (count > 0)
+        CU(cudaMemcpyAsync(e->s.pairs, pairs_ij, sizeof(long long) * 2 * count, cudaMemcpyHostToDevice, e->stream));
+    CU(launch_set_overlaps(e->s, (int)count, overflowed ? 1 : 0, e->stream));
+    ++e->launches;
+    CU(cudaStreamSynchronize(e->stream));      // the host list may be reused by the caller
+    return ORB_OK;
+}
+
+int orb_step_end(orb_engine* e) {
+    LOCK(e);
+    if (!e->sharded) return fail(ORB_ERR_INVALID, "orb_step_end closes a sharded step; orb_step_kick closes an unsharded one");
+    const bool resolve = e->detect && e->p.device_contacts;
+    const bool ordered_u = e->mode == ORB_MODE_FAITHFUL && e->s.n <= 4096;
+    int launches = 0;
+    CU(launch_step_end(e->s, e->p, resolve, ordered_u, e->stream, &launches));
+    e->launches += launches;
+    return ORB_OK;
+}
+
+int orb_contact_stats(orb_engine* e, int64_t* contacts_total, int64_t* full_sweeps) {
+    LOCK(e);
+    CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (contacts_total) *contacts_total = e->h_ctl->contacts_total;
+    if (full_sweeps) *full_sweeps = e->h_ctl->full_sweeps;
     return ORB_OK;
 }
 

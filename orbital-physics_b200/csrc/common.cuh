@@ -24,10 +24,15 @@ struct Ctl {
     double u_stash;
     long long contacts_total; // touching pairs resolved on the device since the last orb_step began
     unsigned int rows_done;   // CTAs of faithful_rows_kernel<true> that finished their tail (last one advances)
+    int pairs_cap;            // capacity of the pair list (set once at allocation, never reset)
+    int full_sweeps;          // contact sweeps that fell back to the list-free lexicographic scan (list overflow)
     int pad_;
 };
 
-constexpr int kOverlapCap = 1 << 16;   // recorded pairs per halting step
+// Pair-list capacity per step: 2^20 pairs (16 MiB) by default; ORBITAL_B200_OVERLAP_CAP overrides (tests force the
+// overflow path with a tiny list).  When a step flags more pairs than fit, the device-side sweep switches to an
+// exact list-free scan (contacts.cuh) and the host-resolved mode sweeps all pairs (core/engine.py).
+constexpr int kOverlapCapDefault = 1 << 20;
 
 // ---------------------------------------------------------------------------
 // Bit-faithful arithmetic.  Every operation is a single
@@ -90,7 +95,7 @@ __device__ __forceinline__ bool overlap_exact(double dx, double dy, double dz, d
 
 __device__ __forceinline__ void record_overlap(Ctl* ctl, long long* pairs, long long i, long long j) {
     const int slot = atomicAdd(&ctl->overlap_count, 1);
-    if (slot < kOverlapCap) {
+    if (slot < ctl->pairs_cap) {
         pairs[2 * slot] = i;
         pairs[2 * slot + 1] = j;
     } else {

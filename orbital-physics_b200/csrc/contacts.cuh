@@ -11,6 +11,8 @@
 // as NumPy does), and, if a body was pushed out, have the whole CTA scan its later pairs for new overlaps and
 // queue them.  A pair that was never flagged and whose bodies never moved cannot be touching, so the visited
 // set equals the reference's -- the same argument as core/physics.py::ObjectCollection.resolve_contacts (host).
+// If the pair list ever overflows (Ctl::pairs_cap), the sweep continues list-free from the current pair
+// (full_sweep_block): slower, but still exactly the reference's loop.
 #pragma once
 #include "common.cuh"
 
@@ -66,6 +68,49 @@ __device__ inline void collide_pair_dev(long long a, long long b, double4* pos4,
     }
 }
 
+// List-free continuation of the sweep (the pair list overflowed, so it can no longer be trusted to hold every
+// candidate): the reference's own loop (physics.py:513-518) from the pair after `cursor` on -- for each row i the CTA
+// finds the smallest j >= jstart that touches i AT THE CURRENT POSITIONS, one thread collides it, and the scan
+// of the row resumes behind it.  Pairs that do not touch are no-ops in the reference, so visiting only the touching
+// ones in lexicographic order is the same sweep.  O(n^2 / blockDim) per call: a fallback, not a fast path.
+__device__ inline int full_sweep_block(double4* pos4, double* vel, long long n, const double* radius,
+                                       const uint8_t* vf32, double restitution, unsigned long long cursor,
+                                       unsigned long long* s_best) {
+    const unsigned long long kNone = ~0ull;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    int hits = 0;
+    long long i = cursor ? (long long)((cursor - 1) / n) : 0;
+    long long jstart = cursor ? (long long)((cursor - 1) % n) + 1 : 1;
+    for (; i < n - 1; ++i, jstart = i + 1) {
+        for (;;) {
+            if (tid == 0) *s_best = kNone;
+            __syncthreads();
+            const double4 pi = pos4[i];
+            const double Ri = radius[i];
+            for (long long j = jstart + tid; j < n; j += nth) {
+                const double4 pj = pos4[j];
+                if (overlap_exact(__dsub_rn(pi.x, pj.x), __dsub_rn(pi.y, pj.y), __dsub_rn(pi.z, pj.z), Ri, radius[j])) {
+                    atomicMin(s_best, (unsigned long long)j);       // ascending per thread: the first hit is its smallest
+                    break;
+                }
+            }
+            __syncthreads();
+            const unsigned long long j = *s_best;
+            __syncthreads();                                        // everyone has read s_best before it is reset
+            if (j == kNone) break;
+            if (tid == 0) {
+                bool moved;
+                collide_pair_dev(i, (long long)j, pos4, vel, n, radius, vf32, restitution, &moved);
+                __threadfence_block();
+            }
+            ++hits;
+            jstart = (long long)j + 1;
+            __syncthreads();
+        }
+    }
+    return hits;
+}
+
 // Replay of the lexicographic sweep over the flagged pairs, executed by every thread of one CTA.
 // `scratch` : 4 x 8 bytes of shared memory.  Returns (in every thread) the number of touching pairs processed.
 __device__ inline int resolve_contacts_block(double4* pos4, double* vel, long long n, const double* radius,
@@ -77,12 +122,22 @@ __device__ inline int resolve_contacts_block(double4* pos4, double* vel, long lo
     unsigned long long* s_moved = scratch + 2;     // the two bodies of the last contact if they were pushed out
     unsigned long long* s_hits = scratch + 3;
     const int tid = threadIdx.x, nth = blockDim.x;
+    const int cap = ctl->pairs_cap;
     if (tid == 0) { *s_cursor = 0; *s_hits = 0; }
     __syncthreads();
     for (;;) {
+        if (*(volatile int*)&ctl->overlap_overflow > 0) {
+            // a pair was dropped (by the force pass, or by the re-queue below): finish without the list
+            const unsigned long long cursor = *s_cursor;
+            __syncthreads();
+            const int more = full_sweep_block(pos4, vel, n, radius, vf32, restitution, cursor, s_best);
+            if (tid == 0) { *s_hits += more; ctl->full_sweeps += 1; }
+            __syncthreads();
+            break;
+        }
         if (tid == 0) { *s_best = kNone; *s_moved = kNone; }
         __syncthreads();
-        const int count = min(*(volatile int*)&ctl->overlap_count, kOverlapCap);
+        const int count = min(*(volatile int*)&ctl->overlap_count, cap);
         const unsigned long long cursor = *s_cursor;
         unsigned long long best = kNone;
         for (int c = tid; c < count; c += nth) {

@@ -172,11 +172,10 @@ __global__ void __launch_bounds__(256) reduce_slabs_kernel(const double* __restr
 template <int TI, bool DETECT>
 static cudaError_t launch_fast_t(const FastArgs& a, const FastPlan& plan, cudaStream_t st) {
     auto kern = force_fast_kernel<TI, DETECT>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;                                 // the attribute is per device
+    if (attr_set.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     kern<<<plan.grid, plan.block, plan.smem, st>>>(a);
     return cudaGetLastError();
@@ -579,11 +578,10 @@ template <int TW>
 static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool detect, int grid, cudaStream_t st,
                               bool fuse_tail) {
     const int smem = kFaithWarps * (3 * TW * 33 * 8 + TW * 32);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;                                 // the attribute is per device
+    if (attr_set.first()) {
         cudaFuncSetAttribute(force_faithful_kernel<TW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(force_faithful_kernel<TW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
     }
     if (s.invr3) {
         // two passes: pair matrix (each pair's sqrt/div once, overlap test included), then ordered row sums
@@ -594,11 +592,10 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
         else
             faithful_pairs_kernel<false><<<dim3(nb, nb), dim3(32, 8), 0, st>>>(s.pos4, s.radius, s.invr3, s.n,
                                                                                s.invr3_ld, p.eps2, s.ctl, s.pairs);
-        static bool rows_attr = false;
-        if (!rows_attr) {
+        static DeviceOnce rows_attr;
+        if (rows_attr.first()) {
             cudaFuncSetAttribute(faithful_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
             cudaFuncSetAttribute(faithful_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
-            rows_attr = true;
         }
         const RowsTail tail = {s.vel, s.vf32, s.hist, s.hist_cap, p.h};
         if (fuse_tail)

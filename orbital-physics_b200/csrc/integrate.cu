@@ -112,6 +112,7 @@ __global__ void advance_contacts_kernel(Ctl* ctl, long long hist_cap) {
     ctl->steps_done += 1;
     if (hist_cap > 0) ctl->hist_count += 1;
     ctl->overlap_count = 0;                      // the next force pass starts a fresh list
+    ctl->overlap_overflow = 0;
 }
 
 cudaError_t launch_contacts(const DeviceState& s, const StepParams& p, bool ordered_potential, cudaStream_t st,
@@ -152,8 +153,42 @@ cudaError_t launch_kick_drift(const DeviceState& s, const StepParams& p, cudaStr
 
 cudaError_t launch_kick_hist(const DeviceState& s, const StepParams& p, cudaStream_t st) {
     const long long nt = s.tgt_hi - s.tgt_lo;
+    // a sharded handle appends the whole snapshot in launch_step_end, after the contacts of all ranks are resolved
+    const bool sharded = !(s.tgt_lo == 0 && s.tgt_hi == s.n);
     kick_hist_kernel<<<grid_for(nt, 256), 256, 0, st>>>(s.pos4, s.vel, s.acc, s.vf32, s.n, s.tgt_lo, s.tgt_hi, p.h,
-                                                        s.hist, s.hist_cap, s.ctl);
+                                                        s.hist, sharded ? 0 : s.hist_cap, s.ctl);
+    return cudaGetLastError();
+}
+
+// End of a sharded step (engine.py:85-92 once every rank holds the same positions, velocities and pair list):
+// replicated contact sweep, history append of ALL n bodies, step bookkeeping.
+cudaError_t launch_step_end(const DeviceState& s, const StepParams& p, bool resolve, bool ordered_potential,
+                            cudaStream_t st, int* launches) {
+    if (resolve) {
+        if (ordered_potential) {
+            contacts_stash_u_kernel<<<1, 256, 0, st>>>(s.pos4, (int)s.n, p.eps2, p.G, s.ctl);
+            if (launches) ++*launches;
+        }
+        contacts_resolve_kernel<<<1, 256, 0, st>>>(s.pos4, s.vel, s.n, s.radius, s.vf32, p.restitution, s.ctl, s.pairs);
+        if (launches) ++*launches;
+    }
+    if (s.hist_cap > 0) {
+        hist_append_kernel<<<grid_for(s.n, 256), 256, 0, st>>>(s.pos4, s.n, s.hist, s.hist_cap, s.ctl);
+        if (launches) ++*launches;
+    }
+    advance_contacts_kernel<<<1, 1, 0, st>>>(s.ctl, s.hist_cap);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// the merged pair list of all ranks was uploaded: make it this handle's list
+__global__ void ctl_set_overlaps_kernel(Ctl* ctl, int count, int overflow) {
+    ctl->overlap_count = count;
+    ctl->overlap_overflow = overflow;
+}
+
+cudaError_t launch_set_overlaps(const DeviceState& s, int count, int overflow, cudaStream_t st) {
+    ctl_set_overlaps_kernel<<<1, 1, 0, st>>>(s.ctl, count, overflow);
     return cudaGetLastError();
 }
 
@@ -520,12 +555,11 @@ cudaError_t launch_tiny_steps(const DeviceState& s, const StepParams& p, long lo
     const int stash = 1;          // the fused kernels only run in faithful mode: `last_potential` is reference-ordered
     if (n <= kMicroMax) {
         const size_t msmem = micro_smem(n);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;                             // the attribute is per device
+        if (attr_set.first()) {
             const int cap = (int)micro_smem(kMicroMax);
             cudaFuncSetAttribute(micro_steps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
             cudaFuncSetAttribute(micro_steps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-            attr_set = true;
         }
         if (detect)
             micro_steps_kernel<true><<<1, block, msmem, st>>>(s.pos4, s.vel, s.acc, s.radius, s.vf32, n, nsteps, p.h,

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace orb {
@@ -18,7 +20,8 @@ struct DeviceState {
     double* radius = nullptr; // n
     uint8_t* vf32 = nullptr;  // n : velocity stored as float32 in the reference
     Ctl* ctl = nullptr;
-    long long* pairs = nullptr;     // 2 x kOverlapCap
+    long long* pairs = nullptr;     // 2 x pairs_cap (Ctl::pairs_cap)
+    int pairs_cap = 0;
     double* hist = nullptr;         // hist_cap x n x 3
     long long hist_cap = 0;
     double* scratch = nullptr;      // fast kernel partial sums: slabs x 3 x n_tgt
@@ -37,6 +40,18 @@ struct StepParams {
     double restitution;       // collide_spheres restitution (core/engine.py:85)
     int device_contacts;      // 1: contacts are resolved on the device, the step never halts
     double uniform_mass;      // the common mass when every body has the same (non-zero) mass, else 0
+};
+
+// "Has this been done on the current device yet?" -- cudaFuncSetAttribute is per device, and one process may
+// drive engines on several GPUs.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        return (mask.fetch_or(bit) & bit) == 0;
+    }
 };
 
 // Geometry chosen for the fast force kernel.
@@ -73,6 +88,10 @@ cudaError_t launch_advance(const DeviceState& s, cudaStream_t st);
 cudaError_t launch_contacts(const DeviceState& s, const StepParams& p, bool ordered_potential, cudaStream_t st,
                             int* launches);
 cudaError_t launch_hist_append(const DeviceState& s, cudaStream_t st);
+// sharded step tail: replicated contact sweep (resolve), full-snapshot history append, bookkeeping
+cudaError_t launch_step_end(const DeviceState& s, const StepParams& p, bool resolve, bool ordered_potential,
+                            cudaStream_t st, int* launches);
+cudaError_t launch_set_overlaps(const DeviceState& s, int count, int overflow, cudaStream_t st);
 // single-CTA fused multi-step kernel (faithful arithmetic), n <= kTinyMax
 constexpr int kTinyMax = 512;        // capacity of the fused kernels
 int tiny_limit();                    // sizes that actually take them (<= kTinyMax; ORBITAL_B200_TINY_MAX overrides)

@@ -175,15 +175,29 @@ class FakeDeviceSystem:
 
 
 class FakeShardedDevice:
-    """CPU stand-in for a *sharded* DeviceSystem (orb_create_sharded / orb_step_begin / orb_step_finish)."""
+    """CPU stand-in for one rank's *sharded* DeviceSystem (orb_create_ranked and the split-step entry points):
+    per-rank force rows, overlap flags and kicks from the oracle, the replicated contact sweep from the
+    oracle's own handle_collisions restatement."""
 
-    def __init__(self, n, device=0, mode=0, tgt_lo=0, tgt_hi=None):
+    def __init__(self, n, device=0, mode=0, tgt_lo=0, tgt_hi=None, rank=None, world=None):
         self.n, self.lo, self.hi = int(n), int(tgt_lo), int(n if tgt_hi is None else tgt_hi)
+        self.device, self.mode = device, mode
+        self.world = int(world or 1)
         self.orc = load_c_oracle()
-        self.pos4 = np.zeros((self.n, 4))
+        cap = self.world * (-(-self.n // self.world))
+        self.pos4 = np.zeros((cap, 4))
         self.vel = np.zeros((3, self.n))
         self.acc = np.zeros((3, self.n))
+        self.radius = np.zeros(self.n)
+        self.f32 = np.zeros(self.n, bool)
         self.partial = False       # True: emulate the pair-symmetric sharding (partial acc on every rank)
+        self.restitution = 1.0
+        self.local_pairs = np.empty((0, 2), dtype=np.int64)
+        self.merged = np.empty((0, 2), dtype=np.int64)
+        self.contacts_total = 0
+        self.hist_cap, self.hist, self.hist_total = 0, [], 0
+        self.u_stash = None
+        self.launches = 0
 
     def close(self):
         pass
@@ -191,13 +205,29 @@ class FakeShardedDevice:
     def set_params(self, dt, eps, G=6.67430e-11):
         self.dt, self.eps, self.G = float(dt), float(eps), float(G)
 
+    def set_contacts(self, restitution, on_device):
+        assert on_device
+        self.restitution = float(restitution)
+
+    def set_history(self, capacity):
+        self.hist_cap, self.hist, self.hist_total = int(capacity), [], 0
+
     def set_stream(self, s):
         pass
 
+    def set_mode(self, mode):
+        self.mode = mode
+
     def upload(self, x, y, z, vx, vy, vz, m, radius, vel_is_f32=None):
-        self.pos4[:, 0], self.pos4[:, 1], self.pos4[:, 2], self.pos4[:, 3] = x, y, z, m
+        n = self.n
+        self.pos4[:n, 0], self.pos4[:n, 1], self.pos4[:n, 2], self.pos4[:n, 3] = x, y, z, m
         self.vel[0], self.vel[1], self.vel[2] = vx, vy, vz
-        self.f32 = np.zeros(self.n, bool) if vel_is_f32 is None else np.asarray(vel_is_f32, bool)
+        self.radius = np.array(radius, dtype=np.float64, copy=True)
+        self.f32 = np.zeros(n, bool) if vel_is_f32 is None else np.asarray(vel_is_f32, bool).copy()
+
+    def _cols(self):
+        p = self.pos4[: self.n]
+        return [np.ascontiguousarray(p[:, k]) for k in range(4)]
 
     def accel(self):
         rows = np.arange(self.lo, self.hi, dtype=np.int64)
@@ -205,11 +235,24 @@ class FakeShardedDevice:
             # partial accelerations of ALL bodies whose sum over ranks is the full field: this rank
             # contributes the rows of its own slab and zeros elsewhere (bit-exact after the all-reduce)
             self.acc[:] = 0.0
-        p = self.pos4
-        a = self.orc.pairwise_sample(np.ascontiguousarray(p[:, 0]), np.ascontiguousarray(p[:, 1]),
-                                     np.ascontiguousarray(p[:, 2]), np.ascontiguousarray(p[:, 3]),
-                                     self.eps, self.G, rows)
+        x, y, z, m = self._cols()
+        a = self.orc.pairwise_sample(x, y, z, m, self.eps, self.G, rows)
         self.acc[:, self.lo:self.hi] = a.T
+        self.u_stash = None
+        self.launches += 1
+
+    def step_force(self):
+        self.accel()
+        out = []
+        if (self.radius > 0).any():
+            P = self.pos4[: self.n, :3]
+            for i in range(self.lo, self.hi):
+                d = P[i] - P[i + 1:]
+                for k in range(d.shape[0]):
+                    if np.linalg.norm(d[k]) <= self.radius[i] + self.radius[i + 1 + k]:
+                        out.append((i, i + 1 + k))
+        self.local_pairs = np.array(out, dtype=np.int64).reshape(-1, 2)
+        self.merged = self.local_pairs
 
     def _kick(self):
         s = slice(self.lo, self.hi)
@@ -227,13 +270,41 @@ class FakeShardedDevice:
         step = v * self.dt
         step[:, f] = (v[:, f].astype(np.float32) * np.float32(self.dt)).astype(np.float64)
         self.pos4[s, :3] = self.pos4[s, :3] + step.T
+        self.launches += 1
 
     def step_finish(self):
-        self.accel()
+        self.step_force()
         self._kick()
 
     def step_kick(self):
         self._kick()
+        self.launches += 1
+
+    def overlap_count(self):
+        return len(self.local_pairs), False
+
+    def overlap_pairs(self, cap=1 << 16):
+        return self.local_pairs[:cap][::-1].copy(), len(self.local_pairs)
+
+    def set_overlap_pairs(self, pairs, overflowed=False):
+        self.merged = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+
+    def step_end(self):
+        if len(self.merged):
+            x, y, z, m = self._cols()
+            if self.n <= 4096:
+                self.u_stash = self.orc.potential(x, y, z, m, self.eps, self.G)
+            vx, vy, vz = (np.ascontiguousarray(self.vel[k]) for k in range(3))
+            hits = self.orc.lib.orc_collisions(self.n, x, y, z, vx, vy, vz, m, np.ascontiguousarray(self.radius),
+                                               self.f32.astype(np.uint8), self.restitution)
+            self.contacts_total += int(hits)
+            self.pos4[: self.n, 0], self.pos4[: self.n, 1], self.pos4[: self.n, 2] = x, y, z
+            self.vel[0], self.vel[1], self.vel[2] = vx, vy, vz
+        self.local_pairs = self.merged = np.empty((0, 2), dtype=np.int64)
+        self.history_append()
+
+    def contact_stats(self):
+        return {"contacts_total": self.contacts_total, "full_sweeps": 0}
 
     def acc_needs_allreduce(self):
         return self.partial
@@ -242,8 +313,21 @@ class FakeShardedDevice:
         pass
 
     def download_state(self, out=None):
-        return {"x": self.pos4[:, 0].copy(), "y": self.pos4[:, 1].copy(), "z": self.pos4[:, 2].copy(),
+        n = self.n
+        return {"x": self.pos4[:n, 0].copy(), "y": self.pos4[:n, 1].copy(), "z": self.pos4[:n, 2].copy(),
                 "vx": self.vel[0].copy(), "vy": self.vel[1].copy(), "vz": self.vel[2].copy()}
+
+    def download_acc(self):
+        return self.acc.copy()
+
+    def upload_acc(self, a):
+        self.acc[:] = np.asarray(a, dtype=np.float64)
+
+    def potential(self):
+        if self.u_stash is not None:
+            return self.u_stash
+        x, y, z, m = self._cols()
+        return self.orc.potential(x, y, z, m, self.eps, self.G)
 
     def energy_angmom(self):
         s = slice(self.lo, self.hi)
@@ -251,3 +335,25 @@ class FakeShardedDevice:
         K = float(np.sum(0.5 * m * (self.vel[:, s] ** 2).sum(0)))
         L = np.cross(self.pos4[s, :3], (m * self.vel[:, s]).T).sum(0)
         return K, L
+
+    def history_count(self):
+        return self.hist_total
+
+    def history_append(self):
+        if self.hist_cap <= 0:
+            return
+        self.hist.append(self.pos4[: self.n, :3].copy())
+        self.hist = self.hist[-self.hist_cap:]
+        self.hist_total += 1
+
+    def history_download(self, last_k):
+        k = min(int(last_k), len(self.hist))
+        if k <= 0:
+            return np.empty((0, self.n, 3))
+        return np.stack(self.hist[-k:])
+
+    def force_kernel_info(self):
+        return {"name": "fake-sharded", "grid": 1, "block": 32, "smem": 0, "launches_per_step": 4}
+
+    def launch_count(self):
+        return self.launches

@@ -1,8 +1,10 @@
-"""Multi-rank path of core.distributed.ShardedSystem.
+"""Multi-rank path of core.distributed (host-side protocol).
 
-CPU: world_size-2 gloo run over the oracle-backed stand-in (host-side logic: slabs, in-place
-all-gather of packed positions, velocity gather, energy all-reduce).  GPU (`-m gpu`, needs >= 2 GPUs):
-the same scenario on real devices over NCCL, bit-identical to the single-GPU run.
+CPU: world_size-2 gloo runs over the oracle-backed stand-in (slabs incl. ragged ones, in-place all-gather of
+packed positions, partial-acceleration all-reduce, contact lists merged across ranks + replicated sweep,
+velocity gather, energy reduction), and SimulationEngine(devices=[0, 0]) over the in-process communicator.
+GPU (`-m gpu`): tests/test_sharded_gpu.py runs the real per-rank kernels on one device; the NCCL test below needs
+>= 2 GPUs.
 """
 import os
 import socket
@@ -20,58 +22,78 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _scenario(n, kind):
+    """Plummer cloud with every third velocity stored as float32; kind 'contacts' inflates the radii so that
+    several pairs touch (and keep touching) during the run."""
+    from core import synthetic
+    c = synthetic.plummer(n, seed=11)
+    f32 = (np.arange(n) % 3 == 0).astype(np.uint8)
+    vel = [np.where(f32 == 1, v.astype(np.float32).astype(np.float64), v) for v in (c["vx"], c["vy"], c["vz"])]
+    radius = c["radius"].copy()
+    if kind == "contacts":
+        P = np.stack([c["x"], c["y"], c["z"]], 1)
+        d = np.linalg.norm(P[:, None, :] - P[None, :, :], axis=2) + np.eye(n) * 1e300
+        radius[:] = 0.75 * np.sort(d.min(axis=1))[n // 4]      # about a quarter of the bodies start in contact
+    return c, f32, vel, radius
+
+
+def _fake_sharded_class(torch, partial):
+    from core.distributed import ShardedSystem
+    from tests.fake_device import FakeShardedDevice
+
+    class Sys(ShardedSystem):
+        def _make_device(self, rank, lo, hi):
+            d = FakeShardedDevice(self.n, 0, self.mode, lo, hi, rank=rank, world=self.world)
+            d.partial = partial
+            return d
+
+        def _view(self, dev, which, shape):
+            return torch.from_numpy({"pos4": dev.pos4, "vel": dev.vel, "acc": dev.acc}[which])
+
+        def _bind_stream(self, dev):
+            pass
+    return Sys
+
+
 def _worker(rank, world, port, backend, n, steps, out_dir):
     for p in (os.path.join(REPO, "orbital-physics_b200"), REPO):
         if p not in sys.path:
             sys.path.insert(0, p)
     import torch
     import torch.distributed as dist
-    from core import _native, synthetic
-    from core.distributed import ShardedSystem
+    from core import _native
+    from core.distributed import DistComm, ShardedSystem
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group(backend, rank=rank, world_size=world)
-    c = synthetic.plummer(n, seed=11)
-    f32 = (np.arange(n) % 3 == 0).astype(np.uint8)
-    vel = [np.where(f32 == 1, v.astype(np.float32).astype(np.float64), v) for v in (c["vx"], c["vy"], c["vz"])]
+    kind = os.path.basename(out_dir)
+    c, f32, vel, radius = _scenario(n, kind)
     if backend == "gloo":
-        from tests.fake_device import FakeShardedDevice
-
-        class Sys(ShardedSystem):
-            def _make_device(self, mode):
-                d = FakeShardedDevice(self.n, 0, mode, self.lo, self.hi)
-                d.partial = out_dir.endswith("partial")
-                return d
-
-            def _view(self, which, shape):
-                return torch.from_numpy({"pos4": self.dev.pos4, "vel": self.dev.vel, "acc": self.dev.acc}[which])
-
-            def _bind_stream(self):
-                pass
+        Sys = _fake_sharded_class(torch, partial=(kind == "partial"))
         mode = _native.MODE_FAITHFUL
-        sysm = Sys(c["x"], c["y"], c["z"], *vel, c["m"], c["radius"], c["dt"], c["eps"], mode=mode, vel_is_f32=f32)
+        comm = DistComm()
     else:
         torch.cuda.set_device(rank)
-        mode = _native.MODE_FAITHFUL if out_dir.endswith("faithful") else _native.MODE_FAST
-        sysm = ShardedSystem(c["x"], c["y"], c["z"], *vel, c["m"], c["radius"], c["dt"], c["eps"], mode=mode,
-                             device=rank, vel_is_f32=f32)
-    sysm.step(steps)
+        Sys = ShardedSystem
+        mode = _native.MODE_FAITHFUL if kind in ("faithful", "contacts") else _native.MODE_FAST
+        comm = DistComm(device=rank)
+    sysm = Sys.from_arrays(c["x"], c["y"], c["z"], *vel, c["m"], radius, c["dt"], c["eps"], mode=mode, comm=comm,
+                           vel_is_f32=f32)
+    _, resolved = sysm.step(steps)
     st = sysm.gather_state()
     K, L = sysm.energy_angmom()
     if rank == 0:
-        np.savez(os.path.join(out_dir, "result.npz"), K=K, L=L, **st)
+        np.savez(os.path.join(out_dir, "result.npz"), K=K, L=L, resolved=resolved, **st)
     dist.barrier()
     sysm.close()
     dist.destroy_process_group()
 
 
-def _reference(orc, n, steps):
-    from core import synthetic
+def _reference(orc, n, steps, kind="gathered"):
     from oracle.c_oracle import State
-    c = synthetic.plummer(n, seed=11)
-    f32 = (np.arange(n) % 3 == 0).astype(np.uint8)
-    st = State(orc, *c.arrays(), f32, c["dt"], c["eps"])
-    st.step(steps, collisions=False, nthreads=4)
+    c, f32, vel, radius = _scenario(n, kind)
+    st = State(orc, c["x"], c["y"], c["z"], *vel, c["m"], radius, f32, c["dt"], c["eps"])
+    st.step(steps, collisions=(kind == "contacts"), nthreads=1 if kind == "contacts" else 4)
     return st
 
 
@@ -79,60 +101,101 @@ def test_slab_partition():
     from core.distributed import slab
     from core.ensemble import partition
     assert [slab(16, 4, r) for r in range(4)] == [(0, 4), (4, 8), (8, 12), (12, 16)]
+    assert [slab(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]      # ragged: ceil(n / world)
     with pytest.raises(ValueError):
-        slab(10, 4, 0)
+        slab(9, 8, 5)                                                                   # a rank without bodies
     parts = [partition(10, 4, r) for r in range(4)]
     assert parts == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert sum(b - a for a, b in parts) == 10
 
 
-@pytest.mark.parametrize("kind", ["gathered", "partial"])
-def test_two_rank_gloo_matches_single_process(orc, tmp_path, kind):
-    """kind=partial exercises the all-reduce of partial accelerations (pair-symmetric sharding)."""
+@pytest.mark.parametrize("kind,n", [("gathered", 256), ("partial", 256), ("gathered", 251), ("contacts", 96)])
+def test_two_rank_gloo_matches_single_process(orc, tmp_path, kind, n):
+    """kind=partial exercises the all-reduce of partial accelerations (pair-symmetric sharding); n=251 a ragged
+    last slab; kind=contacts the cross-rank pair-list merge and the replicated sweep (engine.py:85)."""
     import torch.multiprocessing as mp
-    n, steps = 256, 4
+    steps = 4
     out = tmp_path / kind
     out.mkdir()
     mp.spawn(_worker, args=(2, _free_port(), "gloo", n, steps, str(out)), nprocs=2, join=True)
     got = np.load(out / "result.npz")
-    st = _reference(orc, n, steps)
+    st = _reference(orc, n, steps, kind)
     for k, ref in (("x", st.x), ("y", st.y), ("z", st.z), ("vx", st.vx), ("vy", st.vy), ("vz", st.vz)):
         assert np.array_equal(got[k], ref), k
-    assert abs(float(got["K"]) - st.kinetic()) <= 1e-9 * st.kinetic()
-    assert np.linalg.norm(got["L"] - st.angmom()) <= 1e-9 * np.linalg.norm(st.angmom()) + 1e-300
+    if kind == "contacts":
+        assert st.hits > 0 and int(got["resolved"]) == st.hits
+    # the device reduction is plain fp64; the oracle's K restates the reference's float32 dot for float32-velocity
+    # bodies (engine.py:107), hence the float32-level tolerance
+    assert abs(float(got["K"]) - st.kinetic()) <= 1e-7 * st.kinetic()
+    assert np.linalg.norm(got["L"] - st.angmom()) <= 1e-7 * np.linalg.norm(st.angmom()) + 1e-300
+
+
+def _patch_fake_sharded(monkeypatch):
+    import torch
+    from core import _native, distributed
+    from tests.fake_device import FakeDeviceSystem
+    monkeypatch.setattr(_native, "DeviceSystem", FakeDeviceSystem)
+    monkeypatch.setattr(distributed, "ShardedSystem", _fake_sharded_class(torch, partial=False))
+
+
+@pytest.mark.parametrize("name", ["coll_dense_mixed", "coll_hit_f32_e05", "mixed12"])
+@pytest.mark.parametrize("use_run", [True, False])
+def test_engine_over_in_process_ranks_matches_reference(golden, monkeypatch, name, use_run):
+    """SimulationEngine(devices=[0, 0, 0]) over a ShardedSystem == the reference's own engine outputs, bit for bit,
+    incl. contacts, U, E, L (host logic over the stand-in; the GPU twin is in tests/test_sharded_gpu.py)."""
+    from core import distributed
+    from tests.test_engine import build_engine, check_against_golden
+    _patch_fake_sharded(monkeypatch)
+    g = golden(name)
+    eng = build_engine(g, devices=[0, 0, 0])
+    assert isinstance(eng._dev, distributed.ShardedSystem) and eng._dev.world == 3
+    check_against_golden(g, eng, use_run=use_run)
+
+
+def test_engine_over_in_process_ranks_history_and_frames(golden, monkeypatch, tmp_path):
+    """run / history / JSONL frames over a ShardedSystem equal the single-device engine."""
+    from core.engine import SimulationEngine, load_frames
+    from core.physics import ObjectCollection
+    from tests.conftest import make_objects
+    _patch_fake_sharded(monkeypatch)
+    g = golden("coll_dense_mixed")
+    kw = dict(dt=float(g["dt"]), softening=float(g["eps"]), restitution=float(g["restitution"]), max_hist=None,
+              cache_every_n=3)
+    steps = 10
+    one = SimulationEngine(ObjectCollection(make_objects(g)), cache_fp=str(tmp_path / "one.jsonl"), **kw)
+    many = SimulationEngine(ObjectCollection(make_objects(g)), cache_fp=str(tmp_path / "many.jsonl"),
+                            devices="0,0", **kw)
+    assert many._dev.world == 2
+    one.run(steps)
+    many.run(steps)
+    for a, b in zip(one.objects, many.objects):
+        assert np.array_equal(a.position(), b.position()) and np.array_equal(a.velocity, b.velocity)
+        assert a.velocity.dtype == b.velocity.dtype
+    u = many.objects[5].uuid
+    assert many.history[u] == one.history[one.objects[5].uuid] and len(many.history[u]) == steps + 1
+    f1, f2 = load_frames(str(tmp_path / "one.jsonl")), load_frames(str(tmp_path / "many.jsonl"))
+    assert len(f1) == len(f2) > 0
+    assert [o["coordinates"] for o in f1[-1]["objects"]] == [o["coordinates"] for o in f2[-1]["objects"]]
+    with pytest.raises(ValueError):
+        SimulationEngine(ObjectCollection(make_objects(g)), cache=False, devices=2, contacts="host")
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("mode", ["faithful", "fast"])
-def test_multi_rank_nccl_matches_single_gpu(orc, tmp_path, mode, world):
+@pytest.mark.parametrize("kind", ["faithful", "fast", "faithful_contacts"])
+def test_multi_rank_nccl_matches_single_gpu(orc, tmp_path, kind, world):
     import torch
     if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+        pytest.skip(f"needs {world} GPUs (the same kernels run on one GPU in tests/test_sharded_gpu.py)")
     import torch.multiprocessing as mp
-    from core import _native, synthetic
-    n, steps = 4096, 3
-    out = tmp_path / mode
+    n, steps = (4096, 3) if kind != "faithful_contacts" else (600, 4)
+    out = tmp_path / ("contacts" if kind == "faithful_contacts" else kind)
     out.mkdir()
     mp.spawn(_worker, args=(world, _free_port(), "nccl", n, steps, str(out)), nprocs=world, join=True)
     got = np.load(out / "result.npz")
-    # single-GPU run of the same kernels through the split-step entry points
-    c = synthetic.plummer(n, seed=11)
-    f32 = (np.arange(n) % 3 == 0).astype(np.uint8)
-    vel = [np.where(f32 == 1, v.astype(np.float32).astype(np.float64), v) for v in (c["vx"], c["vy"], c["vz"])]
-    dev = _native.DeviceSystem(n, 0, _native.MODE_FAITHFUL if mode == "faithful" else _native.MODE_FAST)
-    dev.set_params(c["dt"], c["eps"], c["G"])
-    dev.upload(c["x"], c["y"], c["z"], *vel, c["m"], c["radius"], f32)
-    dev.accel()
-    for _ in range(steps):
-        dev.step_begin(); dev.accel(); dev.step_kick()
-    one = dev.download_state()
-    if mode == "faithful":
-        st = _reference(orc, n, steps)
-        assert np.array_equal(got["x"], st.x) and np.array_equal(got["vx"], st.vx)
-    for k in ("x", "y", "z", "vx", "vy", "vz"):
-        if mode == "faithful":
-            assert np.array_equal(got[k], one[k]), k
-        else:   # the pair blocks are summed in a different order on 2 ranks -> last-bit differences only
-            assert np.allclose(got[k], one[k], rtol=1e-12, atol=0), k
-    dev.close()
+    st = _reference(orc, n, steps, "contacts" if kind == "faithful_contacts" else "gathered")
+    for k, ref in (("x", st.x), ("y", st.y), ("z", st.z), ("vx", st.vx), ("vy", st.vy), ("vz", st.vz)):
+        if kind.startswith("faithful"):
+            assert np.array_equal(got[k], ref), k
+        else:
+            assert np.allclose(got[k], ref, rtol=1e-11, atol=0), k
