@@ -259,7 +259,7 @@ def test_pair_list_overflow_falls_back_to_exact_full_sweep(nat, orc, n, world, m
     from oracle.c_oracle import State
     monkeypatch.setenv("ORBITAL_B200_OVERLAP_CAP", "8")
     x, y, z, vel, m, radius, f32 = contact_scene(n, 99 + n)
-    radius = radius * (3.0 if n < 100 else 1.6)           # crowded: many more than 8 touching pairs per step
+    radius = radius * {48: 6.0, 200: 3.0, 700: 2.5}[n]        # crowded: 20-80 touching pairs per step (oracle)
     st = State(orc, x, y, z, *vel, m, radius, f32, 2.0, 10.0, G, restitution=0.9)
     if world == 1:
         dev = nat.DeviceSystem(n, 0, nat.MODE_FAITHFUL)
