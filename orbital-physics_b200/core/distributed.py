@@ -150,7 +150,8 @@ class ShardedSystem:
         self._detect = False
         self._acc_full = True
         self.steps_done = 0
-        self.comm_events = None        # set to a list to collect (start, end) CUDA events around the collectives
+        self.events = None             # set to {} to collect (start, end) CUDA events per phase: "gather", "reduce",
+                                       # "force" (bench.py); rank-local handles only
 
     @classmethod
     def from_arrays(cls, x, y, z, vx, vy, vz, m, radius, dt, eps, G=6.67430e-11, mode=_native.MODE_FAST,
@@ -245,24 +246,28 @@ class ShardedSystem:
         self._acc_full = True
 
     # -- stepping -----------------------------------------------------------
-    def _timed(self, fn):
-        if self.comm_events is None:
+    def _timed(self, phase, fn):
+        if self.events is None:
             return fn()
         ev = self.torch.cuda.Event
         a, b = ev(enable_timing=True), ev(enable_timing=True)
         a.record()
         fn()
         b.record()
-        self.comm_events.append((a, b))
+        self.events.setdefault(phase, []).append((a, b))
 
     def _all_gather_positions(self):
         if self.world > 1:
-            self._timed(lambda: self.comm.all_gather_rows(self._pos4, self.per))
+            self._timed("gather", lambda: self.comm.all_gather_rows(self._pos4, self.per))
 
     def _reduce_acc(self):
         if self._partial:
-            self._timed(lambda: self.comm.all_reduce_sum(self._acc))
+            self._timed("reduce", lambda: self.comm.all_reduce_sum(self._acc))
         self._acc_full = self._partial or self.world == 1
+
+    def _force_pass(self):
+        for d in self.devs:
+            d.step_force()
 
     def accel(self):
         """Constructor force pass (engine.py:41): no overlap test."""
@@ -292,8 +297,7 @@ class ShardedSystem:
             for d in self.devs:
                 d.step_begin()
             self._all_gather_positions()
-            for d in self.devs:
-                d.step_force()
+            self._timed("force", self._force_pass)
             self._reduce_acc()
             for d in self.devs:
                 d.step_kick()
