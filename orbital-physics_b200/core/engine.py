@@ -117,9 +117,11 @@ class SimulationEngine:
         self._bound = []
         self._uuids = []
         self._index = {}
-        self._snap = None
+        self._snap = None               # host copy of what the device holds (SoA), refreshed by _pull
+        self._pull_epoch = 0            # bumped by every _pull; an Object is current iff its _stamp equals it
         self._device_ahead = False
-        self._host_exposed = False
+        self._touched = {}              # slot -> Object materialised / written since the last host->device sync
+        self._watch = {}                # slot -> Object whose velocity ndarray was handed out (may be edited in place)
         self._host_dirty = False
         self._force_version = 0
         self._acc_cache = (None, None)
@@ -189,6 +191,7 @@ class SimulationEngine:
         for o in self._bound:
             if o._engine is self:
                 o._engine = None
+        self._touched, self._watch = {}, {}
         self._bound = objs
         self._uuids = [o.uuid for o in objs]
         self._index = {u: i for i, u in enumerate(self._uuids)}
@@ -197,6 +200,7 @@ class SimulationEngine:
         self._params = None
         if n == 0:
             self._snap = None
+            self._device_ahead = self._host_dirty = False
             self._acc_cache = (self._force_version, {})
             self._U_cache = (self._force_version, 0.0)
             return
@@ -209,9 +213,11 @@ class SimulationEngine:
         self._drain_mode = limit is None or limit > cap_max
         self._dev.set_history(self._ring_cap)
         self._upload(self._gather())
-        for o in objs:
+        for i, o in enumerate(objs):
             o._engine = self
-        self._device_ahead = self._host_exposed = self._host_dirty = False
+            o._slot = i
+            o._stamp = self._pull_epoch                 # the objects ARE the state that was just uploaded
+        self._device_ahead = self._host_dirty = False
         if initial:
             self._dev.accel()                               # engine.py:41
             self._force_version += 1
@@ -233,55 +239,111 @@ class SimulationEngine:
         return distributed.ShardedSystem(n, mode, self._comm)
 
     # ------------------------------------------------------------ lazy mirroring
-    def _host_read(self):
+    # After a step the device is ahead of the Python objects.  The first attribute read of ANY bound object pulls
+    # the state once (one transfer into self._snap); each object then materialises its own Coordinates / velocity
+    # from that snapshot when it is touched, so reading one body of a 262,144-body engine costs one download, not
+    # 262,144 Python objects.  Objects whose velocity ndarray was handed out are refreshed at every pull and at
+    # the end of every advance, because the reference updates that very array in place (engine.py:70) and callers
+    # may hold on to it -- and may edit it in place, which _push_if_needed picks up.
+    def _host_read(self, obj=None, velocity=False):
         with self._lock:
             if self._device_ahead:
                 self._pull()
-            self._host_exposed = True
+            if obj is not None and obj._engine is self:
+                self._materialize(obj)
+                self._touched[obj._slot] = obj
+                if velocity and obj._slot not in self._watch:
+                    self._watch[obj._slot] = obj
+                    obj._vel_seen = self._vel_key(obj)
 
-    def _host_write(self):
+    def _host_write(self, obj=None):
         with self._lock:
             if self._device_ahead:
                 self._pull()
+            if obj is not None and obj._engine is self:
+                self._materialize(obj)
+                self._touched[obj._slot] = obj
             self._host_dirty = True
 
+    @staticmethod
+    def _vel_key(obj):
+        v = obj._velocity
+        return (float(v[0]), float(v[1]), float(v[2]), str(getattr(v, "dtype", "")))
+
+    def _materialize(self, o):
+        """Bring one bound object up to the last pulled snapshot."""
+        if o._stamp == self._pull_epoch:
+            return
+        i, snap = o._slot, self._snap
+        p, w = snap["pos"], snap["vel"]
+        o._coordinates = Coordinates(x=p[0, i], y=p[1, i], z=p[2, i])     # np.float64 members, like from_iterable
+        v = o._velocity
+        if isinstance(v, np.ndarray) and v.shape == (3,) and v.dtype in (np.float32, np.float64):
+            v[0], v[1], v[2] = w[0, i], w[1, i], w[2, i]                  # in place: dtype and identity kept
+        else:
+            o._velocity = np.array([w[0, i], w[1, i], w[2, i]])
+        o._stamp = self._pull_epoch
+        if i in self._watch:
+            o._vel_seen = self._vel_key(o)
+
+    def _materialize_all(self):
+        for o in self._bound:
+            self._materialize(o)
+
     def _pull(self):
-        """Device -> host mirrors (one transfer)."""
+        """Device -> host snapshot (one transfer); objects follow lazily."""
         st = self._dev.download_state()
-        x, y, z, vx, vy, vz = (st[k] for k in ("x", "y", "z", "vx", "vy", "vz"))
-        for i, o in enumerate(self._bound):
-            o._coordinates = Coordinates(x=x[i], y=y[i], z=z[i])     # np.float64 members, like from_iterable
-            v = o._velocity
-            if isinstance(v, np.ndarray) and v.shape == (3,) and v.dtype in (np.float32, np.float64):
-                v[0], v[1], v[2] = vx[i], vy[i], vz[i]                # in place: dtype and identity kept
-            else:
-                o._velocity = np.array([vx[i], vy[i], vz[i]])
         s = self._snap
-        s["pos"] = np.stack([x, y, z])
-        s["vel"] = np.stack([vx, vy, vz])
+        s["pos"] = np.stack([st["x"], st["y"], st["z"]])
+        s["vel"] = np.stack([st["vx"], st["vy"], st["vz"]])
+        self._pull_epoch += 1
         self._device_ahead = False
+        for o in self._watch.values():
+            self._materialize(o)
 
     def _push_if_needed(self):
-        """Host -> device if the host copy may have been modified since the last sync."""
+        """Host -> device if a touched object differs from the last synchronised snapshot."""
         objs = self.objects.objects
         if len(objs) != len(self._bound) or any(a is not b for a, b in zip(objs, self._bound)):
             if self._device_ahead:
                 self._pull()
+            self._materialize_all()
             self._bind(initial=False)
             return
         if self._dev is None:
             return
         self._sync_params()
-        if not (self._host_exposed or self._host_dirty):
+        if not (self._touched or self._watch or self._host_dirty):
             return
-        g = self._gather()
+        cands = dict(self._watch)
+        cands.update(self._touched)
         s = self._snap
-        same = all(np.array_equal(g[k], s[k]) for k in ("pos", "vel", "m", "radius", "f32"))
-        if not same:
-            if len(self._bound) <= _HOST_DIAG_MAX:
-                self._potential()        # U belongs to the last force build: evaluate before positions change
-            self._upload(g)
-        self._host_exposed = self._host_dirty = False
+        changed = False
+        for i, o in cands.items():
+            if o._stamp != self._pull_epoch:
+                continue                     # never exposed since the last pull: cannot have been edited
+            c = o._coordinates
+            v = o._velocity
+            if not isinstance(v, np.ndarray):
+                v = np.asarray(v, dtype=np.float64)
+            now = (c.x, c.y, c.z, v[0], v[1], v[2], o._mass, o._radius, v.dtype == np.float32)
+            was = (s["pos"][0, i], s["pos"][1, i], s["pos"][2, i], s["vel"][0, i], s["vel"][1, i], s["vel"][2, i],
+                   s["m"][i], s["radius"][i], bool(s["f32"][i]))
+            if not all(a == b for a, b in zip(now, was)):
+                if not changed:
+                    if len(self._bound) <= _HOST_DIAG_MAX:
+                        self._potential()    # U belongs to the last force build: evaluate before positions change
+                    s = {k: np.array(a, copy=True) for k, a in s.items()}
+                    changed = True
+                s["pos"][:, i] = now[0:3]
+                s["vel"][:, i] = now[3:6]
+                s["m"][i], s["radius"][i], s["f32"][i] = now[6], now[7], now[8]
+        if changed:
+            self._upload(s)
+            for o in self._watch.values():
+                o._vel_seen = self._vel_key(o)
+        self._touched = {}
+        self._host_dirty = False
 
     # ------------------------------------------------------------------ history
     def _hist_len(self):
@@ -403,13 +465,16 @@ class SimulationEngine:
             self._potential()                       # U of this force build, before push-out moves bodies
         pairs, count = self._dev.overlap_pairs()
         self._pull()
+        self._materialize_all()                     # the host sweep reads every body
         if count > len(pairs):                      # list overflowed: fall back to the full sweep
             self.objects.handle_collisions(restitution=self.restitution)
         else:
             self.objects.resolve_contacts(pairs, restitution=self.restitution)
         g = self._gather()
         self._upload(g)
-        self._host_exposed = self._host_dirty = False
+        self._touched, self._host_dirty = {}, False
+        for o in self._watch.values():
+            o._vel_seen = self._vel_key(o)
         self._dev.history_append()                  # engine.py:88-92 runs after the collision sweep
 
     def _advance(self, nsteps: int):
@@ -438,6 +503,8 @@ class SimulationEngine:
                 self._resolve_contacts()
             elif done < chunk:
                 raise RuntimeError("device stopped early without reporting a contact")
+        if self._watch:
+            self._pull()                # velocity arrays that were handed out track the state, as in the reference
 
     def _tick(self):
         """Book-keeping after one step (engine.py:94-97)."""
@@ -479,6 +546,15 @@ class SimulationEngine:
             json.dump(state, f)
             f.write('\n')
 
+    def _peek_velocity(self, obj):
+        """obj.velocity for the engine's own read-only use: does not count as handing the array out."""
+        if obj._engine is not self:
+            return obj.velocity
+        if self._device_ahead:
+            self._pull()
+        self._materialize(obj)
+        return obj._velocity
+
     # ---------------------------------------------------------------- diagnostics
     def total_energy(self):
         with self._lock:
@@ -488,7 +564,8 @@ class SimulationEngine:
                 return K + self.last_potential
             K = 0.0
             for obj in self.objects:
-                v2 = float(obj.velocity @ obj.velocity)
+                vel = self._peek_velocity(obj)
+                v2 = float(vel @ vel)
                 K += 0.5 * obj.mass * v2
             return K + self.last_potential
 
@@ -499,7 +576,7 @@ class SimulationEngine:
                 return self._dev.energy_angmom()[1]
             L = np.zeros(3)
             for obj in self.objects:
-                L += np.cross(obj.position(), obj.mass * obj.velocity)
+                L += np.cross(obj.position(), obj.mass * self._peek_velocity(obj))
             return L
 
     # -------------------------------------------------------------------- resume
@@ -550,6 +627,8 @@ class SimulationEngine:
         with self._lock:
             if self._device_ahead:
                 self._pull()
+            if self._dev is not None:
+                self._materialize_all()
             for o in self._bound:
                 if o._engine is self:
                     o._engine = None

@@ -135,6 +135,8 @@ class Object:
                  moi: float = None, angular_velocity: np.ndarray = None, uuid: str = None,
                  unit_profile: UnitProfile = STANDARD, name: str = None):
         self._engine = None            # set by SimulationEngine when the object is bound
+        self._slot = -1                # index in the engine's device arrays
+        self._stamp = -1               # engine pull epoch this object's host copy corresponds to
         self._mass = mass
         self._radius = radius
         self._coordinates = coordinates if coordinates else Coordinates.random()
@@ -148,15 +150,15 @@ class Object:
         self.unit_profile = unit_profile
 
     # -- lazy-mirror plumbing -------------------------------------------------
-    def _before_read(self):
+    def _before_read(self, velocity=False):
         eng = self._engine
         if eng is not None:
-            eng._host_read()
+            eng._host_read(self, velocity)
 
     def _before_write(self):
         eng = self._engine
         if eng is not None:
-            eng._host_write()
+            eng._host_write(self)
 
     @property
     def coordinates(self) -> Coordinates:
@@ -170,7 +172,7 @@ class Object:
 
     @property
     def velocity(self) -> np.ndarray:
-        self._before_read()
+        self._before_read(velocity=True)
         return self._velocity
 
     @velocity.setter

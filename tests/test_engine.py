@@ -243,6 +243,43 @@ def test_host_mutation_between_steps(golden, backend, orc):
     assert eng.objects[1].velocity.dtype == np.float32
 
 
+def test_velocity_array_kept_across_steps_is_live_like_the_reference(golden, backend, orc):
+    """`v = obj.velocity; engine.step(); v += dv; engine.step()`: the reference kicks that very array in place
+    (engine.py:70,82), so `v` tracks the state and the in-place edit is honoured."""
+    from oracle.c_oracle import State
+    g = golden("solar9_f64")
+    eng = build_engine(g)
+    st = State(orc, g["in_x"], g["in_y"], g["in_z"], g["in_vx"], g["in_vy"], g["in_vz"], g["in_m"],
+               g["in_radius"], 0, float(g["dt"]), float(g["eps"]))
+    v = eng.objects[3].velocity                  # handed out once, before any step
+    eng.step(); st.step(1)
+    assert_bits(v, [st.vx[3], st.vy[3], st.vz[3]], "alias follows the step")
+    v += np.array([3.0, -2.0, 0.5])              # never touches the property again
+    st.vx[3] += 3.0; st.vy[3] += -2.0; st.vz[3] += 0.5
+    eng.run(2); st.step(2)
+    assert_bits(v, [st.vx[3], st.vy[3], st.vz[3]], "in-place edit through the alias reached the device")
+    p, vel, a = state_of(eng)
+    assert_bits(p, st.pos); assert_bits(vel, st.vel); assert_bits(a, st.acc)
+    assert eng.objects[3].velocity is v
+
+
+def test_objects_materialise_lazily(golden, backend):
+    """Reading one body after a step pulls the state once and builds that body only."""
+    g = golden("solar15_f64")
+    eng = build_engine(g)
+    eng.run(10)
+    epoch = eng._pull_epoch
+    p7 = eng.objects[7].position()
+    assert eng._pull_epoch == epoch + 1
+    stale = [o for o in eng._bound if o._stamp != eng._pull_epoch]
+    assert len(stale) == len(eng._bound) - 1, "only the body that was read is rebuilt"
+    assert_bits(p7, g["pos_10"][7])
+    assert eng._pull_epoch == epoch + 1, "further reads reuse the snapshot"
+    assert_bits(state_of(eng)[0], g["pos_10"])
+    eng.run(90)
+    assert_bits(state_of(eng)[0], g["pos_100"])
+
+
 def test_late_added_object_raises_keyerror_like_reference(golden, backend):
     from core.physics import Coordinates, Object
     g = golden("solar9_f64")
