@@ -207,6 +207,15 @@ int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int 
 int orb_ens_destroy(orb_ensemble* s);
 int orb_ens_set_params(orb_ensemble* s, double dt, double eps, double G);
 int orb_ens_set_stream(orb_ensemble* s, void* cuda_stream);
+/* Optional per-body attributes, [nsys][nbody] each, NULL = none (call before orb_ens_upload):
+ *   radius      -> every step ends with the reference's contact sweep per system (core/engine.py:85 ->
+ *                  core/physics.py:510-535, 391-422: sequential, lexicographic, in place);
+ *   vel_is_f32  -> per-body "velocity is a float32 array" flags (core/physics.py:184 vs :448-449), overriding
+ *                  the vel_f32 argument of orb_ens_create. */
+int orb_ens_set_bodies(orb_ensemble* s, const double* radius, const uint8_t* vel_is_f32);
+int orb_ens_set_contacts(orb_ensemble* s, double restitution);
+/* Touching pairs resolved since creation (all systems). Synchronous. */
+int orb_ens_contact_count(orb_ensemble* s, int64_t* contacts);
 int orb_ens_upload(orb_ensemble* s, const double* x, const double* y, const double* z,
                    const double* vx, const double* vy, const double* vz, const double* m);
 /* Generate the ensemble's initial condition on the device from orbital elements
@@ -221,12 +230,16 @@ int orb_ens_upload_elements(orb_ensemble* s, const double* M, const double* e, c
                             const double* inc, const double* Omega, const double* omega,
                             const double* m);
 /* fused != 0: all nsteps inside one launch, state in registers/shared memory
- * (FP64-bound); fused == 0: one launch per step, state round-trips HBM
- * (152 B per body-step incl. the accelerations the reference keeps between
- * steps, engine.py:41,78; HBM-bound). Asynchronous. */
+ * (FP64-bound); fused == 0: one launch per step, state round-trips HBM (HBM-bound).
+ * Between the launches of one call only x and the half-kicked velocity travel (read x,u,m +
+ * write x,u = 104 B per body-step); the first launch also reads and the last also
+ * writes the accelerations the reference keeps between steps (engine.py:41,78), so the state is
+ * synchronised (x, v, a) whenever the call returns. Same rounding sequence in both forms.
+ * Asynchronous. */
 int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused);
 int orb_ens_download(orb_ensemble* s, double* x, double* y, double* z,
                      double* vx, double* vy, double* vz);
+int orb_ens_download_acc(orb_ensemble* s, double* ax, double* ay, double* az);   /* each system's engine.acc */
 int orb_ens_energy(orb_ensemble* s, double* E_per_system);
 int orb_ens_synchronize(orb_ensemble* s);
 int orb_ens_launch_count(orb_ensemble* s, int64_t* launches);

@@ -86,6 +86,10 @@ SIGNATURES = {
     "orb_ens_destroy": (C.c_int, [_vp]),
     "orb_ens_set_params": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
     "orb_ens_set_stream": (C.c_int, [_vp, _vp]),
+    "orb_ens_set_bodies": (C.c_int, [_vp, _vp, _vp]),
+    "orb_ens_set_contacts": (C.c_int, [_vp, C.c_double]),
+    "orb_ens_contact_count": (C.c_int, [_vp, _i64p]),
+    "orb_ens_download_acc": (C.c_int, [_vp, _vp, _vp, _vp]),
     "orb_ens_upload": (C.c_int, [_vp] + [_f64] * 7),
     "orb_ens_upload_elements": (C.c_int, [_vp] + [_f64] * 7),
     "orb_ens_step": (C.c_int, [_vp, C.c_int64, C.c_int]),
@@ -438,6 +442,36 @@ class DeviceEnsemble:
             if a.shape != (self.nsys, self.nbody):
                 raise ValueError(f"expected shape ({self.nsys},{self.nbody}), got {a.shape}")
         check(lib().orb_ens_upload(self._h, *[a.reshape(-1) for a in arrs]))
+
+    def set_bodies(self, radius=None, vel_is_f32=None):
+        """Per-body radii (-> contact sweep every step) and float32-velocity flags, [nsys, nbody] each."""
+        shape = (self.nsys, self.nbody)
+        r = f = None
+        if radius is not None:
+            r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, dtype=np.float64), shape))
+        if vel_is_f32 is not None:
+            f = np.ascontiguousarray(np.broadcast_to(np.asarray(vel_is_f32, dtype=np.uint8), shape))
+        check(lib().orb_ens_set_bodies(self._h, r.ctypes.data_as(_vp) if r is not None else None,
+                                       f.ctypes.data_as(_vp) if f is not None else None))
+
+    def set_contacts(self, restitution: float):
+        check(lib().orb_ens_set_contacts(self._h, float(restitution)))
+
+    def contact_count(self) -> int:
+        v = C.c_int64()
+        check(lib().orb_ens_contact_count(self._h, C.byref(v)))
+        return v.value
+
+    def download_acc(self):
+        a = np.empty((3, self.nsys, self.nbody))
+        check(lib().orb_ens_download_acc(self._h, *[_ptr(a[k].reshape(-1)) for k in range(3)]))
+        return a
+
+    def info(self) -> dict:
+        # one step per launch, 16 launches per graph: x,u,m in + x,u out (104 B) per body-step, plus the
+        # accelerations read by the first and written by the last launch of a graph (2 x 24 B / 16)
+        return {"bytes_per_body_step": 104.0 + 48.0 / 16.0,
+                "kernel": "ens_step_fast_kernel" if self.mode == MODE_FAST else "ens_step_kernel"}
 
     def upload_elements(self, M, e, a, inc, Omega, omega, m):
         """Initial condition from orbital elements, generated on the device (orb_ens_upload_elements)."""

@@ -1,9 +1,12 @@
-"""Batched ensemble of independent small systems (BASELINE config C3), one CTA per system.
+"""Batched ensemble of independent small systems (BASELINE config C3).
 
 Semantically `nsys` separate reference `SimulationEngine`s (core/engine.py:19-46,
-65-97 of the reference) advanced in lockstep, without contact handling.  Systems
-are independent, so multi-GPU runs block-partition them with no collectives
-(`partition`).
+65-97 of the reference) advanced in lockstep -- including, when radii are given,
+the contact sweep every engine runs after its step (engine.py:85) and per-body
+velocity dtypes (physics.py:184 vs :448-449).  Bit-exact mode: one warp per
+system; fast mode: nbody/2 lanes per system, 64/nbody systems per warp.
+Systems are independent, so multi-GPU runs block-partition them with no
+collectives (`partition`).
 """
 from __future__ import annotations
 
@@ -54,19 +57,27 @@ class EnsembleEngine:
         return self
 
     def __init__(self, x, y, z, vx, vy, vz, m, dt: float, softening: float = 0.0, *, G: float = 6.67430e-11,
-                 mode: str = "fast", vel_f32: bool = False, device: int | None = None):
+                 mode: str = "fast", vel_f32=False, device: int | None = None, radius=None,
+                 restitution: float = 1.0):
+        """`vel_f32`: bool for all bodies, or a [nsys, nbody] array of per-body flags.
+        `radius`: [nsys, nbody] (or broadcastable); any radius > 0 turns the per-step contact sweep on."""
         x = np.asarray(x, dtype=np.float64)
         if x.ndim != 2:
             raise ValueError("ensemble arrays must be [nsys, nbody]")
         self.nsys, self.nbody = x.shape
         self.dt, self.softening, self.G = float(dt), float(softening), float(G)
         nat_mode = {"fast": _native.MODE_FAST, "faithful": _native.MODE_FAITHFUL}[mode]
-        vel = [np.asarray(a, dtype=np.float64) for a in (vx, vy, vz)]
-        if vel_f32:     # Object.__init__ rounds constructor velocities to float32 (reference physics.py:184)
-            vel = [a.astype(np.float32).astype(np.float64) for a in vel]
+        vel = [np.array(a, dtype=np.float64, copy=True) for a in (vx, vy, vz)]
+        flags = None if np.isscalar(vel_f32) else np.broadcast_to(np.asarray(vel_f32, dtype=bool), x.shape)
+        sel = flags if flags is not None else (np.ones(x.shape, bool) if vel_f32 else np.zeros(x.shape, bool))
+        for a in vel:   # Object.__init__ rounds constructor velocities to float32 (reference physics.py:184)
+            a[sel] = a[sel].astype(np.float32).astype(np.float64)
         self._dev = _native.DeviceEnsemble(self.nsys, self.nbody, default_device() if device is None else device,
-                                           nat_mode, vel_f32)
+                                           nat_mode, bool(vel_f32) if flags is None else False)
         self._dev.set_params(self.dt, self.softening, self.G)
+        if radius is not None or flags is not None:
+            self._dev.set_bodies(radius, flags)
+            self._dev.set_contacts(restitution)
         self._dev.upload(x, y, z, *vel, m)
         self.steps_done = 0
 
@@ -78,6 +89,13 @@ class EnsembleEngine:
     def state(self) -> dict:
         return self._dev.download()
 
+    def acc(self) -> np.ndarray:
+        """[3, nsys, nbody]: every system's accelerations of its last force build (engine.acc)."""
+        return self._dev.download_acc()
+
+    def contacts_resolved(self) -> int:
+        return self._dev.contact_count()
+
     def energy(self) -> np.ndarray:
         return self._dev.energy()
 
@@ -87,5 +105,5 @@ class EnsembleEngine:
     def close(self):
         self._dev.close()
 
-    # algorithmic HBM bytes of one un-fused step: x,y,z,v,a read+write (9*16 B) + m read (8 B) per body
-    BYTES_PER_BODY_STEP = 152
+    # HBM bytes of one un-fused step per body: x, u (half-kicked velocity), m read + x, u written
+    BYTES_PER_BODY_STEP = 104

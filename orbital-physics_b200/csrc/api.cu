@@ -865,6 +865,9 @@ struct orb_ensemble {
     int mode = ORB_MODE_FAST;
     EnsArgs a{};
     double* base = nullptr;     // 10 planes of nsys*nb doubles
+    double* d_radius = nullptr; // optional plane: contact handling (orb_ens_set_bodies)
+    uint8_t* d_vf32 = nullptr;  // optional per-body velocity-dtype flags
+    unsigned long long* d_contacts = nullptr;
     double* d_E = nullptr;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     long long launches = 0;
@@ -879,7 +882,9 @@ void ens_drop_graph(orb_ensemble* s) {
     if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
 }
 
-// small per-GPU batches make the one-step-per-launch mode launch-bound: replay 16 launches as one graph
+// small per-GPU batches make the one-step-per-launch mode launch-bound: replay 16 launches as one graph.
+// The graph starts from and ends with the synchronised (x, v, a) state (first / last, ensemble.cu); the 14
+// launches in between exchange only x and the half-kicked velocity.
 int ens_build_graph(orb_ensemble* s) {
     EnsArgs a = s->a;
     a.nsteps = 1;
@@ -888,8 +893,11 @@ int ens_build_graph(orb_ensemble* s) {
     // the instantiated graph is launched into whatever stream the handle is bound to
     CU(cudaStreamBeginCapture(s->own_stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t ce = cudaSuccess;
-    for (int k = 0; k < kEnsGraphSteps && ce == cudaSuccess; ++k)
+    for (int k = 0; k < kEnsGraphSteps && ce == cudaSuccess; ++k) {
+        a.first = k == 0;
+        a.last = k == kEnsGraphSteps - 1;
         ce = launch_ens_step(a, s->mode == ORB_MODE_FAITHFUL, s->own_stream);
+    }
     cudaError_t ce2 = cudaStreamEndCapture(s->own_stream, &graph);
     if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(ce, "ensemble graph capture"); }
     if (ce2 != cudaSuccess) return cuda_fail(ce2, "cudaStreamEndCapture");
@@ -915,8 +923,14 @@ int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int 
     const long long tot = nsys * (long long)nbody;
     cudaError_t ce = cudaMalloc(&s->base, sizeof(double) * 10 * tot);
     if (ce == cudaSuccess) ce = cudaMalloc(&s->d_E, sizeof(double) * nsys);
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->d_contacts, sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(s->d_contacts, 0, sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
-    if (ce != cudaSuccess) { cudaFree(s->base); cudaFree(s->d_E); delete s; return cuda_fail(ce, "ensemble alloc"); }
+    if (ce != cudaSuccess) {
+        cudaFree(s->base); cudaFree(s->d_E); cudaFree(s->d_contacts);
+        delete s;
+        return cuda_fail(ce, "ensemble alloc");
+    }
     s->stream = s->own_stream;
     double* b = s->base;
     s->a.x = b; s->a.y = b + tot; s->a.z = b + 2 * tot; s->a.vx = b + 3 * tot; s->a.vy = b + 4 * tot;
@@ -927,6 +941,8 @@ int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int 
     while (nbp < nbody) nbp <<= 1;
     s->a.nbp = nbp;
     s->a.vel_f32 = vel_f32 ? 1 : 0;
+    s->a.radius = nullptr; s->a.vf32 = nullptr; s->a.restitution = 1.0; s->a.contacts = s->d_contacts;
+    s->a.first = s->a.last = 1;
     {
         // one warp per system; several systems share a CTA (measured: 1 -> 3.5 TB/s, >= 2 -> 4.1 TB/s)
         const char* env = getenv("ORBITAL_B200_ENS_WARPS");
@@ -944,7 +960,7 @@ int orb_ens_destroy(orb_ensemble* s) {
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
         ens_drop_graph(s);
-        cudaFree(s->base); cudaFree(s->d_E);
+        cudaFree(s->base); cudaFree(s->d_E); cudaFree(s->d_radius); cudaFree(s->d_vf32); cudaFree(s->d_contacts);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;
@@ -955,6 +971,61 @@ int orb_ens_set_params(orb_ensemble* s, double dt, double eps, double G) {
     LOCK(s);
     s->a.dt = dt; s->a.h = 0.5 * dt; s->a.dt32 = (float)dt; s->a.eps2 = eps * eps; s->a.G = G;
     ens_drop_graph(s);
+    return ORB_OK;
+}
+
+int orb_ens_set_bodies(orb_ensemble* s, const double* radius, const uint8_t* vel_is_f32) {
+    LOCK(s);
+    const long long tot = s->a.nsys * (long long)s->a.nb;
+    CU(cudaStreamSynchronize(s->stream));
+    ens_drop_graph(s);
+    bool any_radius = false;
+    if (radius)
+        for (long long i = 0; i < tot && !any_radius; ++i) any_radius = radius[i] > 0.0;
+    // all radii zero: a contact can only be dist == 0, a no-op (physics.py:396) -- no sweep needed
+    if (any_radius) {
+        if (!s->d_radius) CU(cudaMalloc(&s->d_radius, sizeof(double) * tot));
+        CU(cudaMemcpy(s->d_radius, radius, sizeof(double) * tot, cudaMemcpyHostToDevice));
+        s->a.radius = s->d_radius;
+    } else {
+        s->a.radius = nullptr;
+    }
+    if (vel_is_f32 || any_radius) {               // the contact variant always reads per-body flags
+        if (!s->d_vf32) CU(cudaMalloc(&s->d_vf32, (size_t)tot));
+        if (vel_is_f32)
+            CU(cudaMemcpy(s->d_vf32, vel_is_f32, (size_t)tot, cudaMemcpyHostToDevice));
+        else
+            CU(cudaMemset(s->d_vf32, s->a.vel_f32 ? 1 : 0, (size_t)tot));
+        s->a.vf32 = s->d_vf32;
+    } else {
+        s->a.vf32 = nullptr;
+    }
+    return ORB_OK;
+}
+
+int orb_ens_set_contacts(orb_ensemble* s, double restitution) {
+    LOCK(s);
+    s->a.restitution = restitution;
+    ens_drop_graph(s);
+    return ORB_OK;
+}
+
+int orb_ens_contact_count(orb_ensemble* s, int64_t* contacts) {
+    LOCK(s);
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, s->d_contacts, sizeof v, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (contacts) *contacts = (int64_t)v;
+    return ORB_OK;
+}
+
+int orb_ens_download_acc(orb_ensemble* s, double* ax, double* ay, double* az) {
+    LOCK(s);
+    const size_t nb = sizeof(double) * s->a.nsys * s->a.nb;
+    if (ax) CU(cudaMemcpyAsync(ax, s->a.ax, nb, cudaMemcpyDeviceToHost, s->stream));
+    if (ay) CU(cudaMemcpyAsync(ay, s->a.ay, nb, cudaMemcpyDeviceToHost, s->stream));
+    if (az) CU(cudaMemcpyAsync(az, s->a.az, nb, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     return ORB_OK;
 }
 
@@ -1049,6 +1120,7 @@ int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
     const bool faithful = s->mode == ORB_MODE_FAITHFUL;
     if (fused) {
         a.nsteps = nsteps;
+        a.first = a.last = 1;
         if (nsteps > 0) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
     } else {
         a.nsteps = 1;
@@ -1060,7 +1132,13 @@ int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
                 s->launches += kEnsGraphSteps;
             }
         }
-        for (; k < nsteps; ++k) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
+        const int64_t k0 = k;
+        for (; k < nsteps; ++k) {
+            a.first = k == k0;                   // the call (and every graph) starts / ends synchronised
+            a.last = k == nsteps - 1;
+            CU(launch_ens_step(a, faithful, s->stream));
+            ++s->launches;
+        }
     }
     return ORB_OK;
 }

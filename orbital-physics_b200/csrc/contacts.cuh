@@ -18,29 +18,30 @@
 
 namespace orb {
 
-// collide_spheres(obj a, obj b) on the resident state. moved: both bodies were pushed out of overlap.
-__device__ inline void collide_pair_dev(long long a, long long b, double4* pos4, double* vel, long long n,
-                                        const double* radius, const uint8_t* vf32, double restitution, bool* moved) {
-    *moved = false;
-    double4 pa = pos4[a], pb = pos4[b];
-    double nx = __dsub_rn(pa.x, pb.x), ny = __dsub_rn(pa.y, pb.y), nz = __dsub_rn(pa.z, pb.z);   // :394
+// One body as collide_spheres sees it.
+struct ContactBody {
+    double x, y, z, vx, vy, vz, m, R;
+    bool f32;            // velocity is a float32 array in the reference (physics.py:184)
+};
+
+// collide_spheres(obj1 = A, obj2 = B, restitution) -- core/physics.py:391-422 with the reference's rounding
+// sequence.  Returns true when both bodies were pushed out of overlap (their positions changed).
+__device__ inline bool collide_bodies(ContactBody& A, ContactBody& B, double restitution) {
+    double nx = __dsub_rn(A.x, B.x), ny = __dsub_rn(A.y, B.y), nz = __dsub_rn(A.z, B.z);          // :394
     const double dist = __dsqrt_rn(dot3_numpy(nx, ny, nz));                                        // :395
-    if (dist == 0.0) return;                                                                       // :396
+    if (dist == 0.0) return false;                                                                 // :396
     nx = __ddiv_rn(nx, dist); ny = __ddiv_rn(ny, dist); nz = __ddiv_rn(nz, dist);                  // :398
-    const double m1 = pa.w, m2 = pb.w;
-    const bool fa = vf32[a] != 0, fb = vf32[b] != 0;
-    double v1x = vel[a], v1y = vel[a + n], v1z = vel[a + 2 * n];
-    double v2x = vel[b], v2y = vel[b + n], v2z = vel[b + 2 * n];
+    const double m1 = A.m, m2 = B.m;
     double wx, wy, wz;                                       // :401 velocity difference keeps the common dtype
-    if (fa && fb) {
-        wx = (double)__fsub_rn((float)v1x, (float)v2x);
-        wy = (double)__fsub_rn((float)v1y, (float)v2y);
-        wz = (double)__fsub_rn((float)v1z, (float)v2z);
+    if (A.f32 && B.f32) {
+        wx = (double)__fsub_rn((float)A.vx, (float)B.vx);
+        wy = (double)__fsub_rn((float)A.vy, (float)B.vy);
+        wz = (double)__fsub_rn((float)A.vz, (float)B.vz);
     } else {
-        wx = __dsub_rn(v1x, v2x); wy = __dsub_rn(v1y, v2y); wz = __dsub_rn(v1z, v2z);
+        wx = __dsub_rn(A.vx, B.vx); wy = __dsub_rn(A.vy, B.vy); wz = __dsub_rn(A.vz, B.vz);
     }
     const double v_rel = __fma_rn(wz, nz, __fma_rn(wy, ny, __dmul_rn(wx, nx)));   // np.dot -> ddot
-    if (v_rel >= 0.0) return;                                                      // :402 separating
+    if (v_rel >= 0.0) return false;                                                // :402 separating
     const double m1_inv = __ddiv_rn(1.0, m1), m2_inv = __ddiv_rn(1.0, m2);         // :408-409
     double e = restitution;                                                        // :410 np.clip
     e = e < 0.0 ? 0.0 : (e > 1.0 ? 1.0 : e);
@@ -48,23 +49,35 @@ __device__ inline void collide_pair_dev(long long a, long long b, double4* pos4,
     const double j = __ddiv_rn(__dmul_rn(-__dadd_rn(1.0, e), v_rel), inv_sum);     // :412
     const double ix = __dmul_rn(j, nx), iy = __dmul_rn(j, ny), iz = __dmul_rn(j, nz);   // :413
     double t;                                                                      // :414-415 in place, dtype kept
-    t = __dadd_rn(v1x, __ddiv_rn(ix, m1)); vel[a] = fa ? (double)__double2float_rn(t) : t;
-    t = __dadd_rn(v1y, __ddiv_rn(iy, m1)); vel[a + n] = fa ? (double)__double2float_rn(t) : t;
-    t = __dadd_rn(v1z, __ddiv_rn(iz, m1)); vel[a + 2 * n] = fa ? (double)__double2float_rn(t) : t;
-    t = __dsub_rn(v2x, __ddiv_rn(ix, m2)); vel[b] = fb ? (double)__double2float_rn(t) : t;
-    t = __dsub_rn(v2y, __ddiv_rn(iy, m2)); vel[b + n] = fb ? (double)__double2float_rn(t) : t;
-    t = __dsub_rn(v2z, __ddiv_rn(iz, m2)); vel[b + 2 * n] = fb ? (double)__double2float_rn(t) : t;
-    const double overlap = __dsub_rn(__dadd_rn(radius[a], radius[b]), dist);       // :418
-    if (overlap > 0.0) {
-        const double corr = __ddiv_rn(overlap, inv_sum);                           // :420
-        const double c1 = __ddiv_rn(corr, m1), c2 = __ddiv_rn(corr, m2);
-        pa.x = __dadd_rn(pa.x, __dmul_rn(nx, c1)); pa.y = __dadd_rn(pa.y, __dmul_rn(ny, c1));   // :421
-        pa.z = __dadd_rn(pa.z, __dmul_rn(nz, c1));
-        pb.x = __dsub_rn(pb.x, __dmul_rn(nx, c2)); pb.y = __dsub_rn(pb.y, __dmul_rn(ny, c2));   // :422
-        pb.z = __dsub_rn(pb.z, __dmul_rn(nz, c2));
-        pos4[a] = pa;
-        pos4[b] = pb;
-        *moved = true;
+    t = __dadd_rn(A.vx, __ddiv_rn(ix, m1)); A.vx = A.f32 ? (double)__double2float_rn(t) : t;
+    t = __dadd_rn(A.vy, __ddiv_rn(iy, m1)); A.vy = A.f32 ? (double)__double2float_rn(t) : t;
+    t = __dadd_rn(A.vz, __ddiv_rn(iz, m1)); A.vz = A.f32 ? (double)__double2float_rn(t) : t;
+    t = __dsub_rn(B.vx, __ddiv_rn(ix, m2)); B.vx = B.f32 ? (double)__double2float_rn(t) : t;
+    t = __dsub_rn(B.vy, __ddiv_rn(iy, m2)); B.vy = B.f32 ? (double)__double2float_rn(t) : t;
+    t = __dsub_rn(B.vz, __ddiv_rn(iz, m2)); B.vz = B.f32 ? (double)__double2float_rn(t) : t;
+    const double overlap = __dsub_rn(__dadd_rn(A.R, B.R), dist);                   // :418
+    if (!(overlap > 0.0)) return false;
+    const double corr = __ddiv_rn(overlap, inv_sum);                               // :420
+    const double c1 = __ddiv_rn(corr, m1), c2 = __ddiv_rn(corr, m2);
+    A.x = __dadd_rn(A.x, __dmul_rn(nx, c1)); A.y = __dadd_rn(A.y, __dmul_rn(ny, c1));   // :421
+    A.z = __dadd_rn(A.z, __dmul_rn(nz, c1));
+    B.x = __dsub_rn(B.x, __dmul_rn(nx, c2)); B.y = __dsub_rn(B.y, __dmul_rn(ny, c2));   // :422
+    B.z = __dsub_rn(B.z, __dmul_rn(nz, c2));
+    return true;
+}
+
+// collide_spheres(obj a, obj b) on the resident state. moved: both bodies were pushed out of overlap.
+__device__ inline void collide_pair_dev(long long a, long long b, double4* pos4, double* vel, long long n,
+                                        const double* radius, const uint8_t* vf32, double restitution, bool* moved) {
+    const double4 pa = pos4[a], pb = pos4[b];
+    ContactBody A = {pa.x, pa.y, pa.z, vel[a], vel[a + n], vel[a + 2 * n], pa.w, radius[a], vf32[a] != 0};
+    ContactBody B = {pb.x, pb.y, pb.z, vel[b], vel[b + n], vel[b + 2 * n], pb.w, radius[b], vf32[b] != 0};
+    *moved = collide_bodies(A, B, restitution);
+    vel[a] = A.vx; vel[a + n] = A.vy; vel[a + 2 * n] = A.vz;
+    vel[b] = B.vx; vel[b + n] = B.vy; vel[b + 2 * n] = B.vz;
+    if (*moved) {
+        pos4[a] = make_double4(A.x, A.y, A.z, pa.w);
+        pos4[b] = make_double4(B.x, B.y, B.z, pb.w);
     }
 }
 

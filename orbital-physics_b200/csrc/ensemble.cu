@@ -16,6 +16,7 @@
 //             2x2 pairs, keeps its own accelerations and adds the reactions to a travelling accumulator that
 //             rotates one lane per offset (12 SHFL per 4 pairs) and is sent home after the last offset.
 #include "kernels.h"
+#include "contacts.cuh"
 #include "ensemble.h"
 #include "force_common.cuh"
 
@@ -23,25 +24,53 @@ namespace orb {
 
 
 constexpr int kEnsMaxWarps = 8;
+constexpr int kEnsDetectWarps = 4;      // warps per CTA of the variants that carry the contact sweep's shared memory
 
-// reference rounding of the integrator with the velocity dtype fixed at compile time
-template <bool F32>
-__device__ __forceinline__ double ens_kick(double v, double h, double a) {
+// Velocity dtype of the bodies: VM 0 = every velocity is a float64 array, 1 = every velocity is
+// float32 (what Object(...) stores, physics.py:184), 2 = per-body flags (mixed systems, physics.py:448-449).
+template <int VM>
+__device__ __forceinline__ double ens_kick(double v, double h, double a, bool f32) {
     const double r = __dadd_rn(v, __dmul_rn(h, a));
-    return F32 ? (double)__double2float_rn(r) : r;
+    return (VM == 1 || (VM == 2 && f32)) ? (double)__double2float_rn(r) : r;
 }
-template <bool F32>
-__device__ __forceinline__ double ens_drift(double r, double v, double dt, float dt32) {
-    if (F32) return __dadd_rn(r, (double)__fmul_rn(__double2float_rn(v), dt32));
+template <int VM>
+__device__ __forceinline__ double ens_drift(double r, double v, double dt, float dt32, bool f32) {
+    if (VM == 1 || (VM == 2 && f32)) return __dadd_rn(r, (double)__fmul_rn(__double2float_rn(v), dt32));
     return __dadd_rn(r, __dmul_rn(v, dt));
 }
 
-// Faithful mode.  One warp per system; `blockDim.x / 32` systems per CTA (1 = one CTA per system); lane i owns
-// body i and adds its terms in ascending j with the reference's rounding sequence.
+// handle_collisions(restitution) of ONE small system held in shared memory (physics.py:510-535 -> 391-422):
+// the reference's own sequential loop, run by a single lane.  Returns the touching pairs processed.
+__device__ inline int ens_sweep(ContactBody* b, int nb, double restitution) {
+    int hits = 0;
+    for (int i = 0; i < nb; ++i)
+        for (int j = i + 1; j < nb; ++j) {
+            ContactBody& A = b[i];
+            ContactBody& B = b[j];
+            if (overlap_exact(__dsub_rn(A.x, B.x), __dsub_rn(A.y, B.y), __dsub_rn(A.z, B.z), A.R, B.R)) {
+                collide_bodies(A, B, restitution);
+                ++hits;
+            }
+        }
+    return hits;
+}
+
+// What one launch does with the state (`first` / `last` in EnsArgs):
+//   first: the velocity plane holds v_n and the acceleration planes a_n (the synchronised state every
+//          orb_ens_step call starts from and ends with) -> u = kick(v_n, a_n) is formed here;
+//          otherwise the velocity plane already holds u (the half-kicked velocity) and a is not read.
+//   per step: x += dt u; a = F(x); v = kick(u, a); [contacts]; u = kick(v, a) unless this is the very last step.
+//   last:  v_{n+k} and a_{n+k} are written; otherwise only x and u.
+// A one-step-per-launch sequence therefore moves x, u, m in and x, u out per body-step (104 B) instead
+// of 152 B, with exactly the reference's rounding sequence: two separately rounded half-kicks per step.
+
+// Faithful mode.  One warp per system; `blockDim.x / 32` systems per CTA; lane i owns body i and adds its terms in
+// ascending j with the reference's rounding sequence.
 // NBP = bodies rounded up to a power of two (compile time: loops fully unrolled, no index arithmetic).
-template <int NBP, bool F32>
+template <int NBP, int VM, bool DETECT>
 __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsArgs g) {
     __shared__ double4 sp_all[kEnsMaxWarps][NBP];   // {x, y, z, G*m}
+    __shared__ ContactBody cb_all[DETECT ? kEnsDetectWarps : 1][DETECT ? NBP : 1];
     const int warp = threadIdx.x >> 5;
     double4* sp = sp_all[warp];
     const long long sys = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -51,23 +80,28 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsAr
     const bool body = i < nb;
     const long long o = sys * nb + i;
 
-    double x = 0, y = 0, z = 0, m = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0;
+    double x = 0, y = 0, z = 0, m = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, R = 0;
+    bool f32 = VM == 1;
     if (body) {
         x = g.x[o]; y = g.y[o]; z = g.z[o]; m = g.m[o];
         vx = g.vx[o]; vy = g.vy[o]; vz = g.vz[o];
-        ax = g.ax[o]; ay = g.ay[o]; az = g.az[o];
+        if (g.first) { ax = g.ax[o]; ay = g.ay[o]; az = g.az[o]; }
+        if (VM == 2) f32 = g.vf32[o] != 0;
+        if (DETECT) R = g.radius[o];
     }
     const double gm = __dmul_rn(g.G, m);            // G * m (physics.py:151-152)
     const double h = g.h, dt = g.dt, eps2 = g.eps2;
     const float dt32 = g.dt32;
+    if (g.first) {
+        vx = ens_kick<VM>(vx, h, ax, f32);                        // engine.py:69-70
+        vy = ens_kick<VM>(vy, h, ay, f32);
+        vz = ens_kick<VM>(vz, h, az, f32);
+    }
 
     for (long long s = 0; s < g.nsteps; ++s) {
-        vx = ens_kick<F32>(vx, h, ax);                            // engine.py:69-70
-        vy = ens_kick<F32>(vy, h, ay);
-        vz = ens_kick<F32>(vz, h, az);
-        x = ens_drift<F32>(x, vx, dt, dt32);                      // engine.py:73-75
-        y = ens_drift<F32>(y, vy, dt, dt32);
-        z = ens_drift<F32>(z, vz, dt, dt32);
+        x = ens_drift<VM>(x, vx, dt, dt32, f32);                  // engine.py:73-75
+        y = ens_drift<VM>(y, vy, dt, dt32, f32);
+        z = ens_drift<VM>(z, vz, dt, dt32, f32);
         if (i < NBP) sp[i] = make_double4(x, y, z, gm);
         __syncwarp();
         double bx = 0.0, by = 0.0, bz = 0.0;                      // physics.py:132
@@ -76,19 +110,48 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsAr
             for (int j = 0; j < NBP; ++j) {
                 if (j == i || j >= nb) continue;
                 const double4 q = sp[j];
-                pair_faithful(__dsub_rn(q.x, x), __dsub_rn(q.y, y), __dsub_rn(q.z, z), eps2, q.w, bx, by, bz);
+                const double dx = __dsub_rn(q.x, x), dy = __dsub_rn(q.y, y), dz = __dsub_rn(q.z, z);
+                pair_faithful(dx, dy, dz, eps2, q.w, bx, by, bz);
             }
         }
         ax = bx; ay = by; az = bz;
-        vx = ens_kick<F32>(vx, h, ax);                            // engine.py:81-82
-        vy = ens_kick<F32>(vy, h, ay);
-        vz = ens_kick<F32>(vz, h, az);
+        vx = ens_kick<VM>(vx, h, ax, f32);                        // engine.py:81-82
+        vy = ens_kick<VM>(vy, h, ay, f32);
+        vz = ens_kick<VM>(vz, h, az, f32);
         __syncwarp();
+        if (DETECT) {
+            // engine.py:85: every lane publishes its body, lane 0 tests and resolves in the reference's order
+            ContactBody* cb = cb_all[warp];
+            if (body) cb[i] = ContactBody{x, y, z, vx, vy, vz, m, R, f32};
+            __syncwarp();
+            bool any = false;
+            if (body) {
+                for (int j = i + 1; j < nb; ++j)
+                    any |= overlap_exact(__dsub_rn(x, cb[j].x), __dsub_rn(y, cb[j].y), __dsub_rn(z, cb[j].z), R, cb[j].R);
+            }
+            if (__any_sync(0xffffffffu, any)) {
+                if (i == 0) {
+                    const int hits = ens_sweep(cb, nb, g.restitution);
+                    if (g.contacts) atomicAdd(g.contacts, (unsigned long long)hits);
+                }
+                __syncwarp();
+                if (body) {
+                    const ContactBody c = cb[i];
+                    x = c.x; y = c.y; z = c.z; vx = c.vx; vy = c.vy; vz = c.vz;
+                }
+            }
+            __syncwarp();
+        }
+        if (s + 1 < g.nsteps || !g.last) {
+            vx = ens_kick<VM>(vx, h, ax, f32);                    // the next step's first half-kick (engine.py:69-70)
+            vy = ens_kick<VM>(vy, h, ay, f32);
+            vz = ens_kick<VM>(vz, h, az, f32);
+        }
     }
     if (body) {
         g.x[o] = x; g.y[o] = y; g.z[o] = z;
         g.vx[o] = vx; g.vy[o] = vy; g.vz[o] = vz;
-        g.ax[o] = ax; g.ay[o] = ay; g.az[o] = az;
+        if (g.last) { g.ax[o] = ax; g.ay[o] = ay; g.az[o] = az; }
     }
 }
 
@@ -96,8 +159,9 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsAr
 // Fast mode.  NBP = bodies rounded up to a power of two; LPS = NBP/2 lanes per system.
 // Padded bodies (index >= nb) and the bodies of systems past the end get zero mass and a far-away dummy
 // position (distinct per body), so every pair is finite and contributes exactly 0 -- the inner loop needs
-// no predicates.
-template <int NBP, bool F32>
+// no predicates.  DETECT: a conservative per-pair threshold on r^2 (one compare per pair) flags systems that may
+// have a touching pair; those run the exact sequential sweep.
+template <int NBP, int VM, bool DETECT>
 __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const EnsArgs g) {
     constexpr int LPS = NBP / 2;                 // lanes per system
     constexpr int SPW = 32 / LPS;                // systems per warp
@@ -106,6 +170,7 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
     constexpr int STRIDE = 3 * LPS;              // shared-memory stride per system: bank-conflict free for all NBP
     __shared__ double2 sxy_all[kEnsMaxWarps][SPW * STRIDE];
     __shared__ double sz_all[kEnsMaxWarps][SPW * STRIDE];
+    __shared__ ContactBody cb_all[DETECT ? kEnsDetectWarps : 1][DETECT ? SPW * NBP : 1];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int I = lane & LM;
@@ -117,27 +182,36 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
     double2* sxy = sxy_all[warp] + sw * STRIDE;
     double* sz = sz_all[warp] + sw * STRIDE;
 
-    bool has[2];
+    bool has[2], f32[2];
     long long o[2];
-    double x[2], y[2], z[2], m[2], vx[2], vy[2], vz[2], ax[2], ay[2], az[2];
+    double x[2], y[2], z[2], m[2], vx[2], vy[2], vz[2], ax[2], ay[2], az[2], R[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int b = I + k * LPS;
         has[k] = sys < g.nsys && b < nb;
         o[k] = sys * nb + b;
-        x[k] = 1e150 * (double)(b + 1); y[k] = 0.0; z[k] = 0.0; m[k] = 0.0;
+        x[k] = 1e150 * (double)(b + 1); y[k] = 0.0; z[k] = 0.0; m[k] = 0.0; R[k] = 0.0;
         vx[k] = vy[k] = vz[k] = ax[k] = ay[k] = az[k] = 0.0;
+        f32[k] = VM == 1;
         if (has[k]) {
             x[k] = g.x[o[k]]; y[k] = g.y[o[k]]; z[k] = g.z[o[k]]; m[k] = g.m[o[k]];
             vx[k] = g.vx[o[k]]; vy[k] = g.vy[o[k]]; vz[k] = g.vz[o[k]];
-            ax[k] = g.ax[o[k]]; ay[k] = g.ay[o[k]]; az[k] = g.az[o[k]];
+            if (g.first) { ax[k] = g.ax[o[k]]; ay[k] = g.ay[o[k]]; az[k] = g.az[o[k]]; }
+            if (VM == 2) f32[k] = g.vf32[o[k]] != 0;
+            if (DETECT) R[k] = g.radius[o[k]];
         }
     }
-    // partner masses do not change: fetch them once (through the same shared-memory slots)
+    // partner masses (and radii) do not change: fetch them once (through the same shared-memory slots)
     double mj[NS > 0 ? NS : 1][2];
+    double thr[DETECT && NS > 0 ? NS : 1][2][2];     // [offset][partner body][own body]: conservative r^2 bound
     double mi_half[2] = {m[0], m[1]};            // own masses as seen by the antipodal offset
+    const double eps2 = g.eps2;
+    constexpr double kSlack = 1.0 + 9.5367431640625e-07;      // 1 + 2^-20: covers the rounding of either r^2 form
+    double thr_own = 0.0;
+    if (DETECT) { const double rs = R[0] + R[1]; thr_own = fma(rs, rs, eps2) * kSlack; }
     if (NS > 0) {
         sz[I] = m[0]; sz[I + LPS] = m[1];
+        if (DETECT) { sxy[I] = make_double2(R[0], 0.0); sxy[I + LPS] = make_double2(R[1], 0.0); }
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
@@ -146,23 +220,39 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
             mj[t][0] = vt ? sz[J] : 0.0;
             mj[t][1] = vt ? sz[J + LPS] : 0.0;
             if (t + 1 == NS && !vt) mi_half[0] = mi_half[1] = 0.0;
+            if (DETECT) {
+#pragma unroll
+                for (int kj = 0; kj < 2; ++kj)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const double rs = R[k] + sxy[J + kj * LPS].x;
+                        thr[t][kj][k] = vt ? fma(rs, rs, eps2) * kSlack : -1.0;   // the upper half skips the antipodes
+                    }
+            }
         }
         __syncwarp();
     }
-    const double h = g.h, dt = g.dt, eps2 = g.eps2, G = g.G;
+    const double h = g.h, dt = g.dt, G = g.G;
     const float dt32 = g.dt32;
     const int group = lane & ~LM;
+    if (g.first) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (has[k]) {
+                vx[k] = ens_kick<VM>(vx[k], h, ax[k], f32[k]);           // engine.py:69-70
+                vy[k] = ens_kick<VM>(vy[k], h, ay[k], f32[k]);
+                vz[k] = ens_kick<VM>(vz[k], h, az[k], f32[k]);
+            }
+        }
+    }
 
     for (long long s = 0; s < g.nsteps; ++s) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (has[k]) {
-                vx[k] = ens_kick<F32>(vx[k], h, ax[k]);                  // engine.py:69-70
-                vy[k] = ens_kick<F32>(vy[k], h, ay[k]);
-                vz[k] = ens_kick<F32>(vz[k], h, az[k]);
-                x[k] = ens_drift<F32>(x[k], vx[k], dt, dt32);            // engine.py:73-75
-                y[k] = ens_drift<F32>(y[k], vy[k], dt, dt32);
-                z[k] = ens_drift<F32>(z[k], vz[k], dt, dt32);
+                x[k] = ens_drift<VM>(x[k], vx[k], dt, dt32, f32[k]);     // engine.py:73-75
+                y[k] = ens_drift<VM>(y[k], vy[k], dt, dt32, f32[k]);
+                z[k] = ens_drift<VM>(z[k], vz[k], dt, dt32, f32[k]);
             }
             if (NS > 0) {
                 sxy[I + k * LPS] = make_double2(x[k], y[k]);
@@ -170,10 +260,12 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
             }
         }
         if (NS > 0) __syncwarp();
+        bool flag = false;
         double a0x, a0y, a0z, a1x, a1y, a1z;
         {   // the lane's own pair (I, I + LPS)
             const double dx = x[1] - x[0], dy = y[1] - y[0], dz = z[1] - z[0];
             const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+            if (DETECT) flag |= r2 <= thr_own;
             int hi;
             const double s0 = inv_r3_plain(r2, hi);
             const double si = s0 * m[1], sj = s0 * m[0];
@@ -197,14 +289,18 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
                 int hi;
                 {
                     const double dx = pxy.x - x[0], dy = pxy.y - y[0], dz = pz - z[0];
-                    const double s0 = inv_r3_plain(fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2))), hi);
+                    const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+                    if (DETECT) flag |= r2 <= thr[t][kj][0];
+                    const double s0 = inv_r3_plain(r2, hi);
                     const double si = s0 * mjj, sj = s0 * mi0;
                     a0x = fma(si, dx, a0x); a0y = fma(si, dy, a0y); a0z = fma(si, dz, a0z);
                     cx = fma(-sj, dx, cx); cy = fma(-sj, dy, cy); cz = fma(-sj, dz, cz);
                 }
                 {
                     const double dx = pxy.x - x[1], dy = pxy.y - y[1], dz = pz - z[1];
-                    const double s0 = inv_r3_plain(fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2))), hi);
+                    const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+                    if (DETECT) flag |= r2 <= thr[t][kj][1];
+                    const double s0 = inv_r3_plain(r2, hi);
                     const double si = s0 * mjj, sj = s0 * mi1;
                     a1x = fma(si, dx, a1x); a1y = fma(si, dy, a1y); a1z = fma(si, dz, a1z);
                     cx = fma(-sj, dx, cx); cy = fma(-sj, dy, cy); cz = fma(-sj, dz, cz);
@@ -222,19 +318,57 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (has[k]) {
-                vx[k] = ens_kick<F32>(vx[k], h, ax[k]);                  // engine.py:81-82
-                vy[k] = ens_kick<F32>(vy[k], h, ay[k]);
-                vz[k] = ens_kick<F32>(vz[k], h, az[k]);
+                vx[k] = ens_kick<VM>(vx[k], h, ax[k], f32[k]);           // engine.py:81-82
+                vy[k] = ens_kick<VM>(vy[k], h, ay[k], f32[k]);
+                vz[k] = ens_kick<VM>(vz[k], h, az[k], f32[k]);
             }
         }
         if (NS > 0) __syncwarp();
+        if (DETECT) {
+            // engine.py:85 for the systems whose prefilter fired: publish the bodies, one lane per system runs the
+            // reference's sequential sweep with the exact test, everybody reloads
+            const unsigned fired = __ballot_sync(0xffffffffu, flag);
+            if (fired) {
+                const bool mine = ((fired >> group) & ((1u << LPS) - 1u)) != 0u && sys < g.nsys;
+                ContactBody* cb = cb_all[warp] + sw * NBP;
+                if (mine) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        cb[I + k * LPS] = ContactBody{x[k], y[k], z[k], vx[k], vy[k], vz[k], m[k], R[k], f32[k]};
+                }
+                __syncwarp();
+                if (mine && I == 0) {
+                    const int hits = ens_sweep(cb, nb, g.restitution);
+                    if (hits && g.contacts) atomicAdd(g.contacts, (unsigned long long)hits);
+                }
+                __syncwarp();
+                if (mine) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const ContactBody c = cb[I + k * LPS];
+                        x[k] = c.x; y[k] = c.y; z[k] = c.z; vx[k] = c.vx; vy[k] = c.vy; vz[k] = c.vz;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (s + 1 < g.nsteps || !g.last) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (has[k]) {
+                    vx[k] = ens_kick<VM>(vx[k], h, ax[k], f32[k]);       // the next step's first half-kick
+                    vy[k] = ens_kick<VM>(vy[k], h, ay[k], f32[k]);
+                    vz[k] = ens_kick<VM>(vz[k], h, az[k], f32[k]);
+                }
+            }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (has[k]) {
             g.x[o[k]] = x[k]; g.y[o[k]] = y[k]; g.z[o[k]] = z[k];
             g.vx[o[k]] = vx[k]; g.vy[o[k]] = vy[k]; g.vz[o[k]] = vz[k];
-            g.ax[o[k]] = ax[k]; g.ay[o[k]] = ay[k]; g.az[o[k]] = az[k];
+            if (g.last) { g.ax[o[k]] = ax[k]; g.ay[o[k]] = ay[k]; g.az[o[k]] = az[k]; }
         }
     }
 }
@@ -305,29 +439,37 @@ __global__ void __launch_bounds__(32) ens_energy_kernel(const EnsArgs g, double*
     if (i == 0) E[sys] = e;
 }
 
-template <bool FAITHFUL, int NBP>
-static void launch_ens_step_t(const EnsArgs& a, int w, cudaStream_t st) {
+template <bool FAITHFUL, int NBP, int VM, bool DETECT>
+static void launch_ens_variant(const EnsArgs& a, int w, cudaStream_t st) {
+    if (DETECT && w > kEnsDetectWarps) w = kEnsDetectWarps;
     const int block = 32 * w;
     if (FAITHFUL) {
         const unsigned grid = (unsigned)((a.nsys + w - 1) / w);                 // one warp per system
-        if (a.vel_f32)
-            ens_step_kernel<NBP, true><<<grid, block, 0, st>>>(a);
-        else
-            ens_step_kernel<NBP, false><<<grid, block, 0, st>>>(a);
+        ens_step_kernel<NBP, VM, DETECT><<<grid, block, 0, st>>>(a);
     } else {
         const long long per_cta = (long long)w * (64 / NBP);                    // 64/NBP systems per warp
         const unsigned grid = (unsigned)((a.nsys + per_cta - 1) / per_cta);
-        if (a.vel_f32)
-            ens_step_fast_kernel<NBP, true><<<grid, block, 0, st>>>(a);
-        else
-            ens_step_fast_kernel<NBP, false><<<grid, block, 0, st>>>(a);
+        ens_step_fast_kernel<NBP, VM, DETECT><<<grid, block, 0, st>>>(a);
     }
+}
+
+template <bool FAITHFUL, int NBP>
+static void launch_ens_step_t(const EnsArgs& a, int w, cudaStream_t st) {
+    if (a.radius)                     // contacts: always with per-body dtype flags (one variant carries the sweep)
+        launch_ens_variant<FAITHFUL, NBP, 2, true>(a, w, st);
+    else if (a.vf32)
+        launch_ens_variant<FAITHFUL, NBP, 2, false>(a, w, st);
+    else if (a.vel_f32)
+        launch_ens_variant<FAITHFUL, NBP, 1, false>(a, w, st);
+    else
+        launch_ens_variant<FAITHFUL, NBP, 0, false>(a, w, st);
 }
 
 cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st) {
     int w = a.warps_per_cta;
     if (w < 1) w = 1;
     if (w > kEnsMaxWarps) w = kEnsMaxWarps;
+    if (a.radius && !a.vf32) return cudaErrorInvalidValue;       // the contact variant reads the dtype flags
 #define ORB_ENS_CASE(P)                                                       \
     case P:                                                                   \
         if (faithful) launch_ens_step_t<true, P>(a, w, st);                   \

@@ -10,8 +10,13 @@ struct EnsArgs {
     long long nsteps;
     double h, dt, eps2, G;
     float dt32;
-    int vel_f32;
-    int warps_per_cta;     // systems per CTA (one warp each); 1 = one CTA per system
+    int vel_f32;           // every velocity is float32 (ignored when vf32 is set)
+    int warps_per_cta;     // warps per CTA
+    const double* radius;           // [nsys][nb] or nullptr: no contact handling
+    const unsigned char* vf32;      // [nsys][nb] per-body "velocity is float32" flags, or nullptr
+    double restitution;             // collide_spheres' coefficient (core/engine.py:85)
+    unsigned long long* contacts;   // device counter: touching pairs resolved (or nullptr)
+    int first, last;       // see ensemble.cu: does the launch start from / end with the synchronised (x, v, a) state
 };
 cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st);
 cudaError_t launch_ens_accel(const EnsArgs& a, bool faithful, cudaStream_t st);

@@ -473,6 +473,88 @@ def test_ensemble_faithful_bit_exact_and_fast_close(nat, orc):
     fast.close()
 
 
+@pytest.mark.parametrize("nbody", [2, 5, 13, 16, 17, 32])
+def test_ensemble_fast_acceleration_within_tolerance_every_step(nat, orc, nbody):
+    """ens_step_fast_kernel: relative acceleration error <= 1e-12 per step (BASELINE north_star), checked on every
+    body of 48 systems against the oracle at the SAME positions, after un-fused and fused steps, both velocity
+    dtypes -- the ensemble keeps every system's engine.acc (orb_ens_download_acc)."""
+    from core import synthetic
+    from core.ensemble import EnsembleEngine
+    e = synthetic.ensemble(48, nbody)
+    args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
+    worst = 0.0
+    for vel_f32 in (False, True):
+        ens = EnsembleEngine(*args, dt=e["dt"], softening=e["eps"], mode="fast", vel_f32=vel_f32)
+        for fused, k in ((False, 0), (False, 1), (True, 1), (False, 3), (True, 20), (False, 17)):
+            if k:
+                ens.step(k, fused=fused)
+            st, a = ens.state(), ens.acc()
+            for s in range(48):
+                ref, _ = orc.pairwise(st["x"][s], st["y"][s], st["z"][s], e["m"][s], e["eps"], G, 1)
+                err = relerr(np.ascontiguousarray(a[:, s, :].T), ref)
+                worst = max(worst, float(err.max()))
+                assert err.max() <= TOL_FAST, f"nbody={nbody} f32={vel_f32} system {s}: {err.max():.3e}"
+        ens.close()
+    print(f"\nensemble fast kernel nbody={nbody}: max rel acceleration error {worst:.2e}")
+
+
+def _ensemble_contact_scene(nsys, nb, seed):
+    """Crowded small systems: bodies in a box a few radii wide so that several pairs touch in most steps."""
+    rng = np.random.default_rng(seed)
+    sh = (nsys, nb)
+    out = dict(x=rng.uniform(-4e4, 4e4, sh), y=rng.uniform(-4e4, 4e4, sh), z=rng.uniform(-4e4, 4e4, sh),
+               vx=rng.standard_normal(sh) * 300, vy=rng.standard_normal(sh) * 300, vz=rng.standard_normal(sh) * 300,
+               m=np.exp(rng.uniform(np.log(1e14), np.log(1e16), sh)), radius=rng.uniform(2e3, 9e3, sh))
+    out["radius"][::3] = 0.0                                   # every third system has no radii at all
+    out["f32"] = rng.integers(0, 2, sh).astype(np.uint8)       # mixed velocity dtypes inside a system
+    return out
+
+
+@pytest.mark.parametrize("nb", [6, 16, 21])
+def test_ensemble_contacts_and_mixed_dtypes_equal_standalone_engines(nat, orc, nb):
+    """each system == a standalone reference SimulationEngine on its bodies, INCLUDING the
+    contact sweep of engine.py:85 and per-body velocity dtypes.  Bit-exact mode: bit for bit, fused and un-fused;
+    fast mode: same contacts, state within 1e-9."""
+    from core.ensemble import EnsembleEngine
+    from oracle.c_oracle import State
+    nsys, K, dt, eps, rest = 36, 23, 2.0, 10.0, 0.8
+    e = _ensemble_contact_scene(nsys, nb, 100 + nb)
+    vel = {k: np.where(e["f32"] == 1, e[k].astype(np.float32).astype(np.float64), e[k]) for k in ("vx", "vy", "vz")}
+    want = {k: np.empty((nsys, nb)) for k in ("x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az")}
+    hits = 0
+    for s in range(nsys):
+        st = State(orc, e["x"][s], e["y"][s], e["z"][s], vel["vx"][s], vel["vy"][s], vel["vz"][s], e["m"][s],
+                   e["radius"][s], e["f32"][s], dt, eps, G, restitution=rest)
+        st.step(K, collisions=True)
+        hits += st.hits
+        for k in want:
+            want[k][s] = getattr(st, k)
+    assert hits > 10, "the scene must actually produce contacts"
+    args = (e["x"], e["y"], e["z"], vel["vx"], vel["vy"], vel["vz"], e["m"])
+    for fused in (True, False):
+        ens = EnsembleEngine(*args, dt=dt, softening=eps, mode="faithful", vel_f32=e["f32"], radius=e["radius"],
+                             restitution=rest)
+        if fused:
+            ens.step(K, fused=True)
+        else:
+            ens.step(K - 4, fused=False); ens.step(4, fused=True)
+        got, acc = ens.state(), ens.acc()
+        for k in ("x", "y", "z", "vx", "vy", "vz"):
+            assert_bits(got[k], want[k], f"ensemble nb={nb} fused={fused} {k}")
+        for c, k in enumerate(("ax", "ay", "az")):
+            assert_bits(acc[c], want[k], f"ensemble nb={nb} fused={fused} {k}")
+        assert ens.contacts_resolved() == hits
+        ens.close()
+    fast = EnsembleEngine(*args, dt=dt, softening=eps, mode="fast", vel_f32=e["f32"], radius=e["radius"],
+                          restitution=rest)
+    fast.step(K, fused=False)
+    got = fast.state()
+    assert fast.contacts_resolved() == hits
+    for k in ("x", "y", "z"):
+        assert np.abs(got[k] - want[k]).max() <= 1e-9 * np.abs(want[k]).max(), k
+    fast.close()
+
+
 def test_ensemble_odd_sizes(nat, orc):
     from core import synthetic
     from core.ensemble import EnsembleEngine
