@@ -873,6 +873,12 @@ struct orb_ensemble {
     long long launches = 0;
     bool have_state = false;
     cudaGraphExec_t step_graph = nullptr;     // kEnsGraphSteps un-fused steps (one launch each) as one graph
+    bool use_pdl = true;                      // ORBITAL_B200_ENS_PDL=0 turns programmatic dependent launch off
+    int sm_count = 148;
+    int slice = 16;                           // steps per item of the time-sliced fused kernel (ORBITAL_B200_ENS_SLICE, 0 = off)
+    unsigned long long* d_queue = nullptr;    // work queue head + per-group progress of the time-sliced kernel
+    int* d_progress = nullptr;
+    long long progress_len = 0;
 };
 
 namespace {
@@ -896,6 +902,7 @@ int ens_build_graph(orb_ensemble* s) {
     for (int k = 0; k < kEnsGraphSteps && ce == cudaSuccess; ++k) {
         a.first = k == 0;
         a.last = k == kEnsGraphSteps - 1;
+        a.pdl = (k > 0 && s->use_pdl) ? 1 : 0;     // programmatic edge to the previous step of the graph
         ce = launch_ens_step(a, s->mode == ORB_MODE_FAITHFUL, s->own_stream);
     }
     cudaError_t ce2 = cudaStreamEndCapture(s->own_stream, &graph);
@@ -943,6 +950,19 @@ int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int 
     s->a.vel_f32 = vel_f32 ? 1 : 0;
     s->a.radius = nullptr; s->a.vf32 = nullptr; s->a.restitution = 1.0; s->a.contacts = s->d_contacts;
     s->a.first = s->a.last = 1;
+    s->a.pdl = 0;
+    {
+        const char* env = getenv("ORBITAL_B200_ENS_PDL");
+        s->use_pdl = !(env && env[0] == '0');
+        env = getenv("ORBITAL_B200_ENS_SLICE");
+        if (env) s->slice = std::max(0, atoi(env));
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+        s->progress_len = (nsys * (long long)nbp + 63) / 64;        // groups of 64 / nbp systems (one warp each)
+        cudaError_t c2 = cudaMalloc(&s->d_queue, sizeof(unsigned long long));
+        if (c2 == cudaSuccess) c2 = cudaMalloc(&s->d_progress, sizeof(int) * s->progress_len);
+        if (c2 != cudaSuccess) { cudaGetLastError(); s->slice = 0; }
+    }
     {
         // one warp per system; several systems share a CTA (measured: 1 -> 3.5 TB/s, >= 2 -> 4.1 TB/s)
         const char* env = getenv("ORBITAL_B200_ENS_WARPS");
@@ -961,6 +981,7 @@ int orb_ens_destroy(orb_ensemble* s) {
         cudaStreamSynchronize(s->stream);
         ens_drop_graph(s);
         cudaFree(s->base); cudaFree(s->d_E); cudaFree(s->d_radius); cudaFree(s->d_vf32); cudaFree(s->d_contacts);
+        cudaFree(s->d_queue); cudaFree(s->d_progress);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;
@@ -1121,7 +1142,18 @@ int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
     if (fused) {
         a.nsteps = nsteps;
         a.first = a.last = 1;
-        if (nsteps > 0) { CU(launch_ens_step(a, faithful, s->stream)); ++s->launches; }
+        // few warps of work per SM sub-partition: balance them dynamically in time slices (bit-identical result)
+        const bool sliced = !faithful && s->slice > 0 && nsteps >= 2 * s->slice &&
+                            s->progress_len <= (long long)s->sm_count * 4 * 8;
+        if (sliced) {
+            CU(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), s->stream));
+            CU(cudaMemsetAsync(s->d_progress, 0, sizeof(int) * s->progress_len, s->stream));
+            CU(launch_ens_step_sliced(a, s->slice, s->d_queue, s->d_progress, s->sm_count, s->stream));
+            ++s->launches;
+        } else if (nsteps > 0) {
+            CU(launch_ens_step(a, faithful, s->stream));
+            ++s->launches;
+        }
     } else {
         a.nsteps = 1;
         int64_t k = 0;
@@ -1136,6 +1168,7 @@ int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
         for (; k < nsteps; ++k) {
             a.first = k == k0;                   // the call (and every graph) starts / ends synchronised
             a.last = k == nsteps - 1;
+            a.pdl = (k > k0 && s->use_pdl) ? 1 : 0;
             CU(launch_ens_step(a, faithful, s->stream));
             ++s->launches;
         }

@@ -24,6 +24,13 @@ namespace orb {
 
 
 constexpr int kEnsMaxWarps = 8;
+
+// Programmatic dependent launch (sm_90+): a step launch lets the next one start filling the SMs at once
+// (launch_dependents) and waits for its predecessor's memory only right before it reads the state (wait).  In the
+// one-step-per-launch mode of a small batch a launch is a few microseconds of work, about as much as the gap
+// between two dependent launches.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 constexpr int kEnsDetectWarps = 4;      // warps per CTA of the variants that carry the contact sweep's shared memory
 
 // Velocity dtype of the bodies: VM 0 = every velocity is a float64 array, 1 = every velocity is
@@ -71,10 +78,12 @@ template <int NBP, int VM, bool DETECT>
 __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsArgs g) {
     __shared__ double4 sp_all[kEnsMaxWarps][NBP];   // {x, y, z, G*m}
     __shared__ ContactBody cb_all[DETECT ? kEnsDetectWarps : 1][DETECT ? NBP : 1];
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     double4* sp = sp_all[warp];
     const long long sys = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (sys >= g.nsys) return;                      // whole warp exits together
+    pdl_wait();
     const int i = threadIdx.x & 31;
     const int nb = g.nb;
     const bool body = i < nb;
@@ -161,26 +170,22 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_kernel(const EnsAr
 // position (distinct per body), so every pair is finite and contributes exactly 0 -- the inner loop needs
 // no predicates.  DETECT: a conservative per-pair threshold on r^2 (one compare per pair) flags systems that may
 // have a touching pair; those run the exact sequential sweep.
+// One warp advances the SPW systems [sys0, sys0 + SPW) by `nsteps` steps.  sxy_w / sz_w / cb_w: this warp's shared
+// memory.  State loads bypass L1 (__ldcg): the time-sliced kernel below hands a system from one SM to another.
 template <int NBP, int VM, bool DETECT>
-__global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const EnsArgs g) {
+__device__ __forceinline__ void ens_fast_body(const EnsArgs& g, long long sys0, long long nsteps, bool first,
+                                              bool last, double2* sxy_w, double* sz_w, ContactBody* cb_w) {
     constexpr int LPS = NBP / 2;                 // lanes per system
-    constexpr int SPW = 32 / LPS;                // systems per warp
     constexpr int NS = LPS / 2;                  // ring offsets 1..NS (offset NS pairs antipodes: lower half only)
     constexpr int LM = LPS - 1;
     constexpr int STRIDE = 3 * LPS;              // shared-memory stride per system: bank-conflict free for all NBP
-    __shared__ double2 sxy_all[kEnsMaxWarps][SPW * STRIDE];
-    __shared__ double sz_all[kEnsMaxWarps][SPW * STRIDE];
-    __shared__ ContactBody cb_all[DETECT ? kEnsDetectWarps : 1][DETECT ? SPW * NBP : 1];
-    const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int I = lane & LM;
     const int sw = lane / LPS;
-    const long long sys0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * SPW;
-    if (sys0 >= g.nsys) return;                  // whole warp exits together
     const long long sys = sys0 + sw;
     const int nb = g.nb;
-    double2* sxy = sxy_all[warp] + sw * STRIDE;
-    double* sz = sz_all[warp] + sw * STRIDE;
+    double2* sxy = sxy_w + sw * STRIDE;
+    double* sz = sz_w + sw * STRIDE;
 
     bool has[2], f32[2];
     long long o[2];
@@ -194,9 +199,9 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
         vx[k] = vy[k] = vz[k] = ax[k] = ay[k] = az[k] = 0.0;
         f32[k] = VM == 1;
         if (has[k]) {
-            x[k] = g.x[o[k]]; y[k] = g.y[o[k]]; z[k] = g.z[o[k]]; m[k] = g.m[o[k]];
-            vx[k] = g.vx[o[k]]; vy[k] = g.vy[o[k]]; vz[k] = g.vz[o[k]];
-            if (g.first) { ax[k] = g.ax[o[k]]; ay[k] = g.ay[o[k]]; az[k] = g.az[o[k]]; }
+            x[k] = __ldcg(g.x + o[k]); y[k] = __ldcg(g.y + o[k]); z[k] = __ldcg(g.z + o[k]); m[k] = g.m[o[k]];
+            vx[k] = __ldcg(g.vx + o[k]); vy[k] = __ldcg(g.vy + o[k]); vz[k] = __ldcg(g.vz + o[k]);
+            if (first) { ax[k] = __ldcg(g.ax + o[k]); ay[k] = __ldcg(g.ay + o[k]); az[k] = __ldcg(g.az + o[k]); }
             if (VM == 2) f32[k] = g.vf32[o[k]] != 0;
             if (DETECT) R[k] = g.radius[o[k]];
         }
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
     const double h = g.h, dt = g.dt, G = g.G;
     const float dt32 = g.dt32;
     const int group = lane & ~LM;
-    if (g.first) {
+    if (first) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (has[k]) {
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
         }
     }
 
-    for (long long s = 0; s < g.nsteps; ++s) {
+    for (long long s = 0; s < nsteps; ++s) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (has[k]) {
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
             const unsigned fired = __ballot_sync(0xffffffffu, flag);
             if (fired) {
                 const bool mine = ((fired >> group) & ((1u << LPS) - 1u)) != 0u && sys < g.nsys;
-                ContactBody* cb = cb_all[warp] + sw * NBP;
+                ContactBody* cb = cb_w + sw * NBP;
                 if (mine) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
                 __syncwarp();
             }
         }
-        if (s + 1 < g.nsteps || !g.last) {
+        if (s + 1 < nsteps || !last) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (has[k]) {
@@ -368,8 +373,68 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
         if (has[k]) {
             g.x[o[k]] = x[k]; g.y[o[k]] = y[k]; g.z[o[k]] = z[k];
             g.vx[o[k]] = vx[k]; g.vy[o[k]] = vy[k]; g.vz[o[k]] = vz[k];
-            if (g.last) { g.ax[o[k]] = ax[k]; g.ay[o[k]] = ay[k]; g.az[o[k]] = az[k]; }
+            if (last) { g.ax[o[k]] = ax[k]; g.ay[o[k]] = ay[k]; g.az[o[k]] = az[k]; }
         }
+    }
+}
+
+template <int NBP, int VM, bool DETECT>
+__global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const EnsArgs g) {
+    constexpr int SPW = 64 / NBP;                // systems per warp
+    constexpr int SLOTS = SPW * 3 * (NBP / 2);
+    __shared__ double2 sxy_all[kEnsMaxWarps][SLOTS];
+    __shared__ double sz_all[kEnsMaxWarps][SLOTS];
+    __shared__ ContactBody cb_all[DETECT ? kEnsDetectWarps : 1][DETECT ? SPW * NBP : 1];
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5;
+    const long long sys0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * SPW;
+    if (sys0 >= g.nsys) return;                  // whole warp exits together
+    pdl_wait();
+    ens_fast_body<NBP, VM, DETECT>(g, sys0, g.nsteps, g.first != 0, g.last != 0, sxy_all[warp], sz_all[warp],
+                                   cb_all[DETECT ? warp : 0]);
+}
+
+// Time-sliced variant for small batches in fused mode.  With only a few warps of work per SM sub-partition
+// (8,192 16-body systems = 3.46 warps per scheduler on 148 SMs) a static assignment leaves the schedulers that got
+// 3 warps idle a quarter of the time.  Here a fixed crew of warps (one CTA of 4 per SM slot) pulls (group of SPW
+// systems, slice of `slice` steps) items from a queue; slice s of a group is handed out after slice s-1 and waits
+// for it (per-group progress counter), the state travels through global memory (L2) in its synchronised
+// (x, v, a) form, so the arithmetic -- and the result, bit for bit -- is that of the single pass.
+template <int NBP, int VM, bool DETECT>
+__global__ void __launch_bounds__(32 * kEnsDetectWarps) ens_fast_sliced_kernel(const EnsArgs g, int slice,
+                                                                               unsigned long long* queue,
+                                                                               int* progress) {
+    constexpr int SPW = 64 / NBP;
+    constexpr int SLOTS = SPW * 3 * (NBP / 2);
+    __shared__ double2 sxy_all[kEnsDetectWarps][SLOTS];
+    __shared__ double sz_all[kEnsDetectWarps][SLOTS];
+    __shared__ ContactBody cb_all[DETECT ? kEnsDetectWarps : 1][DETECT ? SPW * NBP : 1];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long ngroups = (g.nsys + SPW - 1) / SPW;
+    const long long nseg = (g.nsteps + slice - 1) / slice;
+    const unsigned long long total = (unsigned long long)(ngroups * nseg);
+    for (;;) {
+        unsigned long long id = 0;
+        if (lane == 0) id = atomicAdd(queue, 1ull);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= total) break;
+        const long long seg = (long long)(id / (unsigned long long)ngroups);
+        const long long grp = (long long)(id % (unsigned long long)ngroups);
+        if (seg > 0) {
+            if (lane == 0) {
+                volatile int* p = progress + grp;
+                while (*p < (int)seg) __nanosleep(64);
+                __threadfence();
+            }
+            __syncwarp();
+        }
+        const long long steps = min((long long)slice, g.nsteps - seg * slice);
+        ens_fast_body<NBP, VM, DETECT>(g, grp * SPW, steps, true, true, sxy_all[warp], sz_all[warp],
+                                       cb_all[DETECT ? warp : 0]);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(progress + grp, (int)seg + 1);
     }
 }
 
@@ -442,14 +507,21 @@ __global__ void __launch_bounds__(32) ens_energy_kernel(const EnsArgs g, double*
 template <bool FAITHFUL, int NBP, int VM, bool DETECT>
 static void launch_ens_variant(const EnsArgs& a, int w, cudaStream_t st) {
     if (DETECT && w > kEnsDetectWarps) w = kEnsDetectWarps;
-    const int block = 32 * w;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(32 * w);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = a.pdl ? 1 : 0;
     if (FAITHFUL) {
-        const unsigned grid = (unsigned)((a.nsys + w - 1) / w);                 // one warp per system
-        ens_step_kernel<NBP, VM, DETECT><<<grid, block, 0, st>>>(a);
+        cfg.gridDim = dim3((unsigned)((a.nsys + w - 1) / w));                   // one warp per system
+        cudaLaunchKernelEx(&cfg, ens_step_kernel<NBP, VM, DETECT>, a);
     } else {
         const long long per_cta = (long long)w * (64 / NBP);                    // 64/NBP systems per warp
-        const unsigned grid = (unsigned)((a.nsys + per_cta - 1) / per_cta);
-        ens_step_fast_kernel<NBP, VM, DETECT><<<grid, block, 0, st>>>(a);
+        cfg.gridDim = dim3((unsigned)((a.nsys + per_cta - 1) / per_cta));
+        cudaLaunchKernelEx(&cfg, ens_step_fast_kernel<NBP, VM, DETECT>, a);
     }
 }
 
@@ -485,6 +557,40 @@ cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st) {
     }
 #undef ORB_ENS_CASE
     return cudaGetLastError();
+}
+
+// Fused fast mode for a small batch: the time-sliced kernel (see ens_fast_sliced_kernel).
+template <int NBP>
+static cudaError_t launch_sliced_t(const EnsArgs& a, int slice, unsigned long long* queue, int* progress, int sm_count,
+                                   cudaStream_t st) {
+    const int block = 32 * kEnsDetectWarps;
+    int per_sm = 0;
+#define ORB_SLICED(VMv, DETv)                                                                                   \
+    do {                                                                                                        \
+        auto kern = ens_fast_sliced_kernel<NBP, VMv, DETv>;                                                     \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) \
+            per_sm = 1;                                                                                         \
+        kern<<<sm_count * per_sm, block, 0, st>>>(a, slice, queue, progress);                                   \
+    } while (0)
+    if (a.radius) ORB_SLICED(2, true);
+    else if (a.vf32) ORB_SLICED(2, false);
+    else if (a.vel_f32) ORB_SLICED(1, false);
+    else ORB_SLICED(0, false);
+#undef ORB_SLICED
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ens_step_sliced(const EnsArgs& a, int slice, unsigned long long* queue, int* progress, int sm_count,
+                                   cudaStream_t st) {
+    if (a.radius && !a.vf32) return cudaErrorInvalidValue;
+    switch (a.nbp) {
+        case 2: return launch_sliced_t<2>(a, slice, queue, progress, sm_count, st);
+        case 4: return launch_sliced_t<4>(a, slice, queue, progress, sm_count, st);
+        case 8: return launch_sliced_t<8>(a, slice, queue, progress, sm_count, st);
+        case 16: return launch_sliced_t<16>(a, slice, queue, progress, sm_count, st);
+        case 32: return launch_sliced_t<32>(a, slice, queue, progress, sm_count, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_ens_accel(const EnsArgs& a, bool faithful, cudaStream_t st) {

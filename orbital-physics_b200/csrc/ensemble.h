@@ -16,9 +16,13 @@ struct EnsArgs {
     const unsigned char* vf32;      // [nsys][nb] per-body "velocity is float32" flags, or nullptr
     double restitution;             // collide_spheres' coefficient (core/engine.py:85)
     unsigned long long* contacts;   // device counter: touching pairs resolved (or nullptr)
+    int pdl;               // host only: launch with programmatic stream serialization (overlaps the predecessor's tail)
     int first, last;       // see ensemble.cu: does the launch start from / end with the synchronised (x, v, a) state
 };
 cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st);
+// fast mode, all a.nsteps in one launch, balanced over the SMs in slices of `slice` steps (small batches)
+cudaError_t launch_ens_step_sliced(const EnsArgs& a, int slice, unsigned long long* queue, int* progress, int sm_count,
+                                   cudaStream_t st);
 cudaError_t launch_ens_accel(const EnsArgs& a, bool faithful, cudaStream_t st);
 cudaError_t launch_ens_energy(const EnsArgs& a, double* E, cudaStream_t st);
 // kepler.cu: Keplerian elements -> Cartesian state (core/physics.py:43-71, core/body.py:184-249)

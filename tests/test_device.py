@@ -555,6 +555,30 @@ def test_ensemble_contacts_and_mixed_dtypes_equal_standalone_engines(nat, orc, n
     fast.close()
 
 
+@pytest.mark.parametrize("nb", [5, 16, 32])
+def test_ensemble_time_sliced_fused_kernel_is_bit_identical(nat, monkeypatch, nb):
+    """Small batches in fused mode run ens_fast_sliced_kernel (work queue of (system group, 16-step slice) items,
+    state handed over in its synchronised form): same bits as the single pass and as one launch per step."""
+    from core import synthetic
+    e = synthetic.ensemble(301, nb)
+    args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
+    K = 117                                              # 7 slices of 16 + one of 5
+    outs = []
+    for slice_env, fused in (("16", True), ("0", True), ("16", False), ("7", True)):
+        monkeypatch.setenv("ORBITAL_B200_ENS_SLICE", slice_env)
+        ens = nat.DeviceEnsemble(301, nb, 0, nat.MODE_FAST, vel_f32=True)
+        ens.set_params(e["dt"], e["eps"], e["G"])
+        ens.upload(*[np.asarray(a, dtype=np.float32).astype(np.float64) if i in (3, 4, 5) else a
+                     for i, a in enumerate(args)])
+        ens.step(K, fused=fused)
+        outs.append((ens.download(), ens.download_acc()))
+        ens.close()
+    for st, acc in outs[1:]:
+        for k in st:
+            assert_bits(st[k], outs[0][0][k], f"sliced vs single-pass {k}")
+        assert_bits(acc, outs[0][1], "accelerations")
+
+
 def test_ensemble_odd_sizes(nat, orc):
     from core import synthetic
     from core.ensemble import EnsembleEngine
