@@ -874,8 +874,11 @@ struct orb_ensemble {
     bool have_state = false;
     cudaGraphExec_t step_graph = nullptr;     // kEnsGraphSteps un-fused steps (one launch each) as one graph
     bool use_pdl = true;                      // ORBITAL_B200_ENS_PDL=0 turns programmatic dependent launch off
+    cudaStream_t br_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only: branches of the step graph
+    cudaEvent_t br_event[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_event = nullptr;
     int sm_count = 148;
-    int slice = 16;                           // steps per item of the time-sliced fused kernel (ORBITAL_B200_ENS_SLICE, 0 = off)
+    int slice = 32;                           // steps per item of the time-sliced fused kernel (ORBITAL_B200_ENS_SLICE, 0 = off)
     unsigned long long* d_queue = nullptr;    // work queue head + per-group progress of the time-sliced kernel
     int* d_progress = nullptr;
     long long progress_len = 0;
@@ -883,6 +886,7 @@ struct orb_ensemble {
 
 namespace {
 constexpr int kEnsGraphSteps = 16;
+constexpr int kEnsBranches = 4;          // independent sub-batches of a small ensemble inside one step graph
 
 void ens_drop_graph(orb_ensemble* s) {
     if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
@@ -891,19 +895,65 @@ void ens_drop_graph(orb_ensemble* s) {
 // small per-GPU batches make the one-step-per-launch mode launch-bound: replay 16 launches as one graph.
 // The graph starts from and ends with the synchronised (x, v, a) state (first / last, ensemble.cu); the 14
 // launches in between exchange only x and the half-kicked velocity.
+// the systems [lo, hi) of an ensemble as an ensemble of their own (they are contiguous in every plane)
+EnsArgs ens_subrange(const EnsArgs& a, long long lo, long long hi) {
+    EnsArgs b = a;
+    const long long off = lo * a.nb;
+    b.x += off; b.y += off; b.z += off; b.vx += off; b.vy += off; b.vz += off; b.ax += off; b.ay += off; b.az += off;
+    b.m += off;
+    if (b.radius) b.radius += off;
+    if (b.vf32) b.vf32 += off;
+    b.nsys = hi - lo;
+    return b;
+}
+
 int ens_build_graph(orb_ensemble* s) {
     EnsArgs a = s->a;
     a.nsteps = 1;
     cudaGraph_t graph = nullptr;
+    // A small batch is one wave of warps that all load, then all compute, then all store: a launch is a
+    // dependent latency chain (~4 us at 8,192 systems) with nothing to overlap it.  Cut the batch into
+    // independent branches of the graph -- systems never interact -- so that one branch computes while another
+    // waits on memory.
+    const long long warps = (a.nsys * (long long)a.nbp + 63) / 64;
+    int branches = 1;
+    if (s->mode == ORB_MODE_FAST && warps <= (long long)s->sm_count * 4 * 8) branches = kEnsBranches;
+    {
+        const char* env = getenv("ORBITAL_B200_ENS_BRANCHES");
+        if (env) branches = std::max(1, std::min(kEnsBranches, atoi(env)));
+    }
+    branches = (int)std::min<long long>(branches, a.nsys);
     // capture on the library's own stream (the caller's may be the legacy default stream, which cannot capture);
     // the instantiated graph is launched into whatever stream the handle is bound to
     CU(cudaStreamBeginCapture(s->own_stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t ce = cudaSuccess;
-    for (int k = 0; k < kEnsGraphSteps && ce == cudaSuccess; ++k) {
-        a.first = k == 0;
-        a.last = k == kEnsGraphSteps - 1;
-        a.pdl = (k > 0 && s->use_pdl) ? 1 : 0;     // programmatic edge to the previous step of the graph
-        ce = launch_ens_step(a, s->mode == ORB_MODE_FAITHFUL, s->own_stream);
+    if (branches > 1) {
+        for (int b = 0; b < kEnsBranches && ce == cudaSuccess; ++b) {
+            if (!s->br_stream[b]) ce = cudaStreamCreateWithFlags(&s->br_stream[b], cudaStreamNonBlocking);
+            if (ce == cudaSuccess && !s->br_event[b]) ce = cudaEventCreateWithFlags(&s->br_event[b], cudaEventDisableTiming);
+        }
+        if (ce == cudaSuccess && !s->fork_event) ce = cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventRecord(s->fork_event, s->own_stream);
+        for (int b = 0; b < branches && ce == cudaSuccess; ++b) {
+            const long long lo = a.nsys * b / branches, hi = a.nsys * (b + 1) / branches;
+            EnsArgs sub = ens_subrange(a, lo, hi);
+            ce = cudaStreamWaitEvent(s->br_stream[b], s->fork_event, 0);
+            for (int k = 0; k < kEnsGraphSteps && ce == cudaSuccess; ++k) {
+                sub.first = k == 0;
+                sub.last = k == kEnsGraphSteps - 1;
+                sub.pdl = (k > 0 && s->use_pdl) ? 1 : 0;
+                ce = launch_ens_step(sub, false, s->br_stream[b]);
+            }
+            if (ce == cudaSuccess) ce = cudaEventRecord(s->br_event[b], s->br_stream[b]);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s->own_stream, s->br_event[b], 0);
+        }
+    } else {
+        for (int k = 0; k < kEnsGraphSteps && ce == cudaSuccess; ++k) {
+            a.first = k == 0;
+            a.last = k == kEnsGraphSteps - 1;
+            a.pdl = (k > 0 && s->use_pdl) ? 1 : 0;     // programmatic edge to the previous step of the graph
+            ce = launch_ens_step(a, s->mode == ORB_MODE_FAITHFUL, s->own_stream);
+        }
     }
     cudaError_t ce2 = cudaStreamEndCapture(s->own_stream, &graph);
     if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(ce, "ensemble graph capture"); }
@@ -982,6 +1032,11 @@ int orb_ens_destroy(orb_ensemble* s) {
         ens_drop_graph(s);
         cudaFree(s->base); cudaFree(s->d_E); cudaFree(s->d_radius); cudaFree(s->d_vf32); cudaFree(s->d_contacts);
         cudaFree(s->d_queue); cudaFree(s->d_progress);
+        for (int b = 0; b < 4; ++b) {
+            if (s->br_stream[b]) cudaStreamDestroy(s->br_stream[b]);
+            if (s->br_event[b]) cudaEventDestroy(s->br_event[b]);
+        }
+        if (s->fork_event) cudaEventDestroy(s->fork_event);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;
@@ -1144,7 +1199,7 @@ int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
         a.first = a.last = 1;
         // few warps of work per SM sub-partition: balance them dynamically in time slices (bit-identical result)
         const bool sliced = !faithful && s->slice > 0 && nsteps >= 2 * s->slice &&
-                            s->progress_len <= (long long)s->sm_count * 4 * 8;
+                            s->progress_len <= (long long)s->sm_count * 4 * 4;    // < 4 warps per SM sub-partition
         if (sliced) {
             CU(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), s->stream));
             CU(cudaMemsetAsync(s->d_progress, 0, sizeof(int) * s->progress_len, s->stream));

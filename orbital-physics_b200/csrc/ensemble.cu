@@ -15,6 +15,8 @@
 //             offset s lane I meets the two bodies of lane I+s (positions from shared memory), evaluates the
 //             2x2 pairs, keeps its own accelerations and adds the reactions to a travelling accumulator that
 //             rotates one lane per offset (12 SHFL per 4 pairs) and is sent home after the last offset.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "contacts.cuh"
 #include "ensemble.h"
@@ -565,11 +567,14 @@ static cudaError_t launch_sliced_t(const EnsArgs& a, int slice, unsigned long lo
                                    cudaStream_t st) {
     const int block = 32 * kEnsDetectWarps;
     int per_sm = 0;
+    const char* env = getenv("ORBITAL_B200_ENS_CREW");       // CTAs per SM of the crew (0: all that fit)
+    const int crew = env ? atoi(env) : 3;                     // measured: 3 CTAs (12 warps) per SM beat 4 and 2
 #define ORB_SLICED(VMv, DETv)                                                                                   \
     do {                                                                                                        \
         auto kern = ens_fast_sliced_kernel<NBP, VMv, DETv>;                                                     \
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) \
             per_sm = 1;                                                                                         \
+        if (crew > 0 && crew < per_sm) per_sm = crew;                                                           \
         kern<<<sm_count * per_sm, block, 0, st>>>(a, slice, queue, progress);                                   \
     } while (0)
     if (a.radius) ORB_SLICED(2, true);
