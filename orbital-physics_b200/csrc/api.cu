@@ -873,7 +873,8 @@ struct orb_ensemble {
     long long launches = 0;
     bool have_state = false;
     cudaGraphExec_t step_graph = nullptr;     // kEnsGraphSteps un-fused steps (one launch each) as one graph
-    bool use_pdl = true;                      // ORBITAL_B200_ENS_PDL=0 turns programmatic dependent launch off
+    bool use_pdl = false;                     // ORBITAL_B200_ENS_PDL=1: programmatic dependent launch between the steps
+                                              // (measured: no gain at any batch size, a loss at 4,096 systems)
     cudaStream_t br_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only: branches of the step graph
     cudaEvent_t br_event[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_event = nullptr;
@@ -915,9 +916,12 @@ int ens_build_graph(orb_ensemble* s) {
     // dependent latency chain (~4 us at 8,192 systems) with nothing to overlap it.  Cut the batch into
     // independent branches of the graph -- systems never interact -- so that one branch computes while another
     // waits on memory.
+    // Measured (profiles/r2_ens_branch_sweep*.txt, 16-body systems, us per step for 1 / 3 branches): 16,384 systems
+    // 6.4 / 5.2, 32,768: 11.3 / 9.7, 65,536: 21.0 / 19.3; no gain from 131,072 up (several waves overlap by
+    // themselves) nor at <= 8,192, where a step is bound by the ~3 us a dependent kernel node costs.
     const long long warps = (a.nsys * (long long)a.nbp + 63) / 64;
     int branches = 1;
-    if (s->mode == ORB_MODE_FAST && warps <= (long long)s->sm_count * 4 * 8) branches = kEnsBranches;
+    if (s->mode == ORB_MODE_FAST && warps <= 16384) branches = 3;
     {
         const char* env = getenv("ORBITAL_B200_ENS_BRANCHES");
         if (env) branches = std::max(1, std::min(kEnsBranches, atoi(env)));
@@ -1003,7 +1007,7 @@ int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int 
     s->a.pdl = 0;
     {
         const char* env = getenv("ORBITAL_B200_ENS_PDL");
-        s->use_pdl = !(env && env[0] == '0');
+        s->use_pdl = env && env[0] == '1';
         env = getenv("ORBITAL_B200_ENS_SLICE");
         if (env) s->slice = std::max(0, atoi(env));
         cudaDeviceProp prop{};
