@@ -163,11 +163,28 @@ int enqueue_force(orb_engine* e, bool detect, int* launches) {
     return ORB_OK;
 }
 
-// one full leapfrog step as separate kernels (engine.py:65-97)
-int enqueue_step(orb_engine* e, int* launches) {
-    CU(launch_kick_drift(e->s, e->p, e->stream));
-    ++*launches;
+// fast mode, pair-symmetric kernel, one panel: the reduction launch can carry the rest of the step
+bool sym_tail_ok(orb_engine* e) {
+    if (!(e->mode == ORB_MODE_FAST && sym_applicable(e) && !e->sharded)) return false;
+    if (ensure_plan(e) != ORB_OK) return false;
+    return sym_tail_applicable(e->sym);
+}
+
+// one full leapfrog step as separate kernels (engine.py:65-97).  begin: launch the first half-kick + drift (false
+// when the previous step's reduction already did it); fuse_next: let this step's reduction do it for the next one.
+int enqueue_step(orb_engine* e, int* launches, bool begin = true, bool fuse_next = false) {
+    if (begin) {
+        CU(launch_kick_drift(e->s, e->p, e->stream));
+        ++*launches;
+    }
     const bool contacts_here = e->p.device_contacts && e->detect;
+    if (sym_tail_ok(e)) {
+        // two launches (+ the contact sweep's): force_sym, then reduce + half-kick + history + bookkeeping
+        const int mode = contacts_here ? kSymTailKick : (fuse_next ? kSymTailCloseNext : kSymTailClose);
+        CU(launch_force_sym(e->s, e->p, e->sym, e->detect, e->stream, launches, mode));
+        if (contacts_here) CU(launch_contacts(e->s, e->p, false, e->stream, launches));
+        return ORB_OK;
+    }
     if (e->mode == ORB_MODE_FAITHFUL && !contacts_here) {
         int rc = ensure_plan(e);
         if (rc) return rc;
@@ -203,7 +220,10 @@ int build_graph(orb_engine* e, int steps, cudaGraphExec_t* out) {
     cudaError_t cb = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
     if (cb != cudaSuccess) { e->stream = bound; return cuda_fail(cb, "cudaStreamBeginCapture"); }
     int launches = 0;
-    for (int k = 0; k < steps && rc == ORB_OK; ++k) rc = enqueue_step(e, &launches);
+    // inside a multi-step graph the reduction of step k also starts step k+1 (no contact sweep in between)
+    const bool chain = steps > 1 && sym_tail_ok(e) && !(e->p.device_contacts && e->detect);
+    for (int k = 0; k < steps && rc == ORB_OK; ++k)
+        rc = enqueue_step(e, &launches, k == 0 || !chain, chain && k + 1 < steps);
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     e->stream = bound;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }

@@ -40,6 +40,7 @@ struct SymArgs {
     double* Pj;                // [panel_blocks][3][n]
     long long n;
     int n_tiles;
+    int tile;                  // bodies per source tile: 64, 128 or 256 (<= kTile, the stage size of the ring)
     double eps2;
     double rmax1, rmax2;
     long long rmax1_idx;
@@ -92,7 +93,8 @@ force_sym_kernel(const SymArgs g) {
     constexpr long long B = (long long)kFastThreads * TI;
     const long long i_lo = (long long)it.I * B;
     const long long i_hi = min(i_lo + B, g.n);
-    const int diag_end = (int)min((long long)g.n_tiles, (i_hi + kTile - 1) / kTile);
+    const int tile_n = g.tile;
+    const int diag_end = (int)min((long long)g.n_tiles, (i_hi + tile_n - 1) / tile_n);
     const int ntiles = it.t1 - it.t0;
 
     if (tid == 0) {
@@ -107,8 +109,8 @@ force_sym_kernel(const SymArgs g) {
 
     auto issue = [&](int t) {
         const int s = t % kStages;
-        const long long j0 = (long long)(it.t0 + t) * kTile;
-        const int cnt = (int)min((long long)kTile, g.n - j0);
+        const long long j0 = (long long)(it.t0 + t) * tile_n;
+        const int cnt = (int)min((long long)tile_n, g.n - j0);
         const uint32_t bytes = (uint32_t)cnt * 32u;
         mbar_expect_tx(&full[s], bytes);
         tma_load_1d(tiles + (size_t)s * kTile * 2, g.pos4 + j0, bytes, &full[s]);
@@ -147,8 +149,8 @@ force_sym_kernel(const SymArgs g) {
         mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
         const double2* tile = tiles + (size_t)s * kTile * 2;
         const int tile_index = it.t0 + t;
-        const long long j0 = (long long)tile_index * kTile;
-        const int cnt = (int)min((long long)kTile, g.n - j0);
+        const long long j0 = (long long)tile_index * tile_n;
+        const int cnt = (int)min((long long)tile_n, g.n - j0);
 
         if (tile_index < diag_end) {
             // ---- diagonal tile: one-sided, self-pair masked (both directions are evaluated by their owners)
@@ -247,9 +249,9 @@ _Pragma(ORB_STR(unroll SYM_UNROLL))
             __syncthreads();
             // fixed-order sum of the four warps' contributions to the tile bodies -> P_j[I][j]
             double* out = g.Pj + (long long)it.slot * 3 * g.n + j0;
-            for (int e = tid; e < 3 * kTile; e += kFastThreads) {
-                const int c = e / kTile;
-                const int slot = e - c * kTile;
+            for (int e = tid; e < 3 * tile_n; e += kFastThreads) {
+                const int c = e / tile_n;
+                const int slot = e - c * tile_n;
                 if (slot < cnt) {
                     double v = slab[c * kTile + slot];
 #pragma unroll
@@ -277,22 +279,17 @@ _Pragma(ORB_STR(unroll SYM_UNROLL))
     }
 }
 
-// a[x] (+)= G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{owned I-blocks of this panel before x} P_j[slot][x] )
-// I-blocks are owned cyclically: I = rank + world * k; the panel holds k in [ka, kb).
-__global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restrict__ Pi, const double* __restrict__ Pj,
-                                                         double* acc, long long n, long long B, int chunk_tiles,
-                                                         int n_chunks, int rank, int world, int ka, int kb, double G,
-                                                         int accumulate, const Ctl* ctl) {
-    if (ctl->halted) return;
-    const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (x >= n) return;
+// G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{owned I-blocks of this panel before x} P_j[slot][x] ), fixed order
+__device__ __forceinline__ void sym_reduce_row(const double* __restrict__ Pi, const double* __restrict__ Pj, long long n,
+                                               long long B, int tile, int chunk_tiles, int n_chunks, int rank, int world,
+                                               int ka, int kb, double G, long long x, double (&out)[3]) {
     const long long X = x / B;
-    const long long T = x / kTile;
+    const long long T = x / tile;
     double s[3] = {0.0, 0.0, 0.0};
     if (X % world == rank) {
         const long long kx = (X - rank) / world;
         if (kx >= ka && kx < kb) {
-            const int c_first = (int)(((X * B) / kTile) / chunk_tiles);
+            const int c_first = (int)(((X * B) / tile) / chunk_tiles);
             for (int c = c_first; c < n_chunks; ++c) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s[k] += Pi[((long long)c * 3 + k) * n + x];
@@ -300,7 +297,7 @@ __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restric
         }
     }
     // owned I-blocks that treated x's tile symmetrically: I < nI  <=>  k < ceil((nI - rank) / world)
-    const long long nI = (T * kTile) / B;
+    const long long nI = (T * tile) / B;
     long long kend = nI > rank ? (nI - rank + world - 1) / world : 0;
     if (kend > kb) kend = kb;
     for (long long k = ka; k < kend; ++k) {
@@ -308,9 +305,98 @@ __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restric
         for (int c = 0; c < 3; ++c) s[c] += Pj[((k - ka) * 3 + c) * n + x];
     }
 #pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = G * s[k];
+}
+
+// The rest of the leapfrog step, riding along in the reduction (unsharded engines, one panel): a step is then
+// kick_drift -> force_sym -> reduce, and inside a multi-step graph even the kick_drift of the NEXT step is done here,
+// which leaves two launches per step.  What matters below ~16k bodies, where a launch costs about as much as the
+// arithmetic (a dependent kernel node is ~3 us; the whole N = 4,096 force pass is ~12 us of FP64 work).
+struct SymTail {
+    int kick;              // second half-kick of this step (engine.py:81-82)
+    int close;             // history append + step bookkeeping (engine.py:88-92, advance_kernel)
+    int next;              // first half-kick + drift of the next step (engine.py:69-75), unless this step halts
+    double4* pos4;
+    double* vel;
+    const uint8_t* vf32;
+    double* hist;
+    long long hist_cap;
+    double h, dt;
+    float dt32;
+    Ctl* ctl_rw;
+};
+
+// a[x] (+)= G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{owned I-blocks of this panel before x} P_j[slot][x] )
+// I-blocks are owned cyclically: I = rank + world * k; the panel holds k in [ka, kb).
+__global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restrict__ Pi, const double* __restrict__ Pj,
+                                                         double* acc, long long n, long long B, int tile,
+                                                         int chunk_tiles, int n_chunks, int rank, int world, int ka,
+                                                         int kb, double G, int accumulate, const Ctl* ctl,
+                                                         const SymTail tail) {
+    if (ctl->halted) return;
+    const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (tail.close) {
+        // every thread has read the ring cursor / overlap count before the last CTA to arrive moves them
+        const long long hist_count = ctl->hist_count;
+        const int overlaps = ctl->overlap_count;
+        if (x < n) {
+            double a3[3];
+            sym_reduce_row(Pi, Pj, n, B, tile, chunk_tiles, n_chunks, rank, world, ka, kb, G, x, a3);
+            acc[x] = a3[0]; acc[x + n] = a3[1]; acc[x + 2 * n] = a3[2];
+            const bool f32 = tail.vf32[x] != 0;
+            double vx = kick_faithful(tail.vel[x], tail.h, a3[0], f32);
+            double vy = kick_faithful(tail.vel[x + n], tail.h, a3[1], f32);
+            double vz = kick_faithful(tail.vel[x + 2 * n], tail.h, a3[2], f32);
+            double4 p = tail.pos4[x];
+            if (tail.hist_cap > 0 && overlaps == 0) {        // a halting step appends on the host
+                double* row = tail.hist + ((hist_count % tail.hist_cap) * n + x) * 3;
+                row[0] = p.x; row[1] = p.y; row[2] = p.z;
+            }
+            if (tail.next && overlaps == 0) {                // the next step's first half (no contact in between)
+                vx = kick_faithful(vx, tail.h, a3[0], f32);
+                vy = kick_faithful(vy, tail.h, a3[1], f32);
+                vz = kick_faithful(vz, tail.h, a3[2], f32);
+                p.x = drift_faithful(p.x, vx, tail.dt, tail.dt32, f32);
+                p.y = drift_faithful(p.y, vy, tail.dt, tail.dt32, f32);
+                p.z = drift_faithful(p.z, vz, tail.dt, tail.dt32, f32);
+                tail.pos4[x] = p;
+            }
+            tail.vel[x] = vx; tail.vel[x + n] = vy; tail.vel[x + 2 * n] = vz;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            Ctl* c = tail.ctl_rw;
+            if (atomicAdd(&c->rows_done, 1u) == gridDim.x - 1) {
+                c->rows_done = 0;
+                c->steps_done += 1;
+                if (overlaps > 0)
+                    c->halted = 1;
+                else if (tail.hist_cap > 0)
+                    c->hist_count = hist_count + 1;
+            }
+        }
+        return;
+    }
+    if (x >= n) return;
+    double a3[3];
+    sym_reduce_row(Pi, Pj, n, B, tile, chunk_tiles, n_chunks, rank, world, ka, kb, G, x, a3);
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double v = G * s[k];
-        acc[x + k * n] = accumulate ? acc[x + k * n] + v : v;
+        const double v = accumulate ? acc[x + k * n] + a3[k] : a3[k];
+        acc[x + k * n] = v;
+        a3[k] = v;
+    }
+    if (tail.kick) {                                         // device-resolved contacts follow: kick only
+        const bool f32 = tail.vf32[x] != 0;
+        tail.vel[x] = kick_faithful(tail.vel[x], tail.h, a3[0], f32);
+        tail.vel[x + n] = kick_faithful(tail.vel[x + n], tail.h, a3[1], f32);
+        tail.vel[x + 2 * n] = kick_faithful(tail.vel[x + 2 * n], tail.h, a3[2], f32);
+        if (tail.hist_cap > 0 && ctl->overlap_count == 0) {  // as kick_hist_kernel: a step with contacts appends after the sweep
+            const double4 p = tail.pos4[x];
+            double* row = tail.hist + ((ctl->hist_count % tail.hist_cap) * n + x) * 3;
+            row[0] = p.x; row[1] = p.y; row[2] = p.z;
+        }
     }
 }
 
@@ -371,7 +457,18 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
     p.world = world;
     p.B = (long long)kFastThreads * ti;
     p.nb_I = (int)((n + p.B - 1) / p.B);
-    p.n_tiles = (int)((n + kTile - 1) / kTile);
+    // Source-tile size.  An item is (I-block, chunk of tiles); with 256-body tiles a mid-size system has too few items
+    // to balance over 148 x 2 CTA slots (N = 16,384, TI = 8: 544 items of ~85 us each for a 155 us pass), so small
+    // systems use finer tiles.  The reduction reads one P_i plane per chunk, which bounds how fine is useful.
+    p.tile = n <= 32768 ? 64 : (n <= 65536 ? 128 : kTile);
+    {
+        const char* env_tile = getenv("ORBITAL_B200_SYM_TILE");
+        if (env_tile) {
+            const int v = atoi(env_tile);
+            if (v == 64 || v == 128 || v == 256) p.tile = v;
+        }
+    }
+    p.n_tiles = (int)((n + p.tile - 1) / p.tile);
     int occ = 0;
     switch (ti) {
         case 1: occ = sym_occupancy<1, false>(); break;
@@ -395,7 +492,7 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
     long long want_chunks = (64 * slots + p.panel_blocks - 1) / p.panel_blocks;
     const char* env_c = getenv("ORBITAL_B200_SYM_CHUNKS");
     if (env_c) want_chunks = atoi(env_c);
-    want_chunks = std::max<long long>(1, std::min<long long>(std::min<long long>(want_chunks, 128), p.n_tiles));
+    want_chunks = std::max<long long>(1, std::min<long long>(std::min<long long>(want_chunks, 512), p.n_tiles));
     p.chunk_tiles = (int)((p.n_tiles + want_chunks - 1) / want_chunks);
     p.n_chunks = (p.n_tiles + p.chunk_tiles - 1) / p.chunk_tiles;
     cudaError_t e;
@@ -408,7 +505,7 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
         std::vector<SymItem> items;
         for (int k = pan.ka; k < pan.kb; ++k) {
             const int I = rank + world * k;
-            const int first_tile = (int)(((long long)I * p.B) / kTile);
+            const int first_tile = (int)(((long long)I * p.B) / p.tile);
             for (int c = first_tile / p.chunk_tiles; c < p.n_chunks; ++c) {
                 SymItem it;
                 it.I = I;
@@ -437,11 +534,22 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
 bool sym_uniform(const SymPlan& p, const StepParams& sp) {
     const char* v = getenv("ORBITAL_B200_SYM_UNI");      // "0": keep the per-pair mass multiplies (cross-check)
     const bool off = v && v[0] == '0';
-    return !off && sp.uniform_mass != 0.0 && p.n % kTile == 0 && p.n % p.B == 0;
+    return !off && sp.uniform_mass != 0.0 && p.n % p.tile == 0 && p.n % p.B == 0;
 }
 
+bool sym_tail_applicable(const SymPlan& p) { return p.world == 1 && p.panels.size() == 1; }
+
 cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const SymPlan& p, bool detect,
-                             cudaStream_t st, int* launches) {
+                             cudaStream_t st, int* launches, int tail_mode) {
+    SymTail tail = {};
+    if (tail_mode != kSymTailNone) {
+        if (!sym_tail_applicable(p)) return cudaErrorInvalidValue;
+        tail.kick = tail_mode == kSymTailKick;
+        tail.close = tail_mode == kSymTailClose || tail_mode == kSymTailCloseNext;
+        tail.next = tail_mode == kSymTailCloseNext;
+        tail.pos4 = s.pos4; tail.vel = s.vel; tail.vf32 = s.vf32; tail.hist = s.hist; tail.hist_cap = s.hist_cap;
+        tail.h = sp.h; tail.dt = sp.dt; tail.dt32 = sp.dt32; tail.ctl_rw = s.ctl;
+    }
     SymArgs a;
     a.pos4 = s.pos4;
     a.radius = s.radius;
@@ -449,6 +557,7 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
     a.Pj = p.Pj;
     a.n = s.n;
     a.n_tiles = p.n_tiles;
+    a.tile = p.tile;
     a.eps2 = sp.eps2;
     a.rmax1 = sp.rmax1;
     a.rmax2 = sp.rmax2;
@@ -481,8 +590,8 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
 #undef ORB_SYM_CASE
         if (e != cudaSuccess) return e;
         const int grid = (int)((s.n + 255) / 256);
-        reduce_sym_kernel<<<grid, 256, 0, st>>>(p.Pi, p.Pj, s.acc, s.n, p.B, p.chunk_tiles, p.n_chunks, p.rank, p.world,
-                                                pan.ka, pan.kb, scale, first ? 0 : 1, s.ctl);
+        reduce_sym_kernel<<<grid, 256, 0, st>>>(p.Pi, p.Pj, s.acc, s.n, p.B, p.tile, p.chunk_tiles, p.n_chunks, p.rank, p.world,
+                                                pan.ka, pan.kb, scale, first ? 0 : 1, s.ctl, tail);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (launches) *launches += 2;
         first = false;

@@ -28,6 +28,7 @@ struct SymPlan {
     int rank = 0, world = 1;  // cyclic ownership of I-blocks (multi-GPU); 0/1 on one GPU
     long long B = 0;          // bodies per I-block (128 * ti)
     int nb_I = 0, n_tiles = 0;
+    int tile = 256;           // bodies per source tile (64 / 128 / 256)
     int chunk_tiles = 0, n_chunks = 0;
     int panel_blocks = 0;
     int ctas_per_sm = 0;
@@ -38,8 +39,16 @@ struct SymPlan {
 
 cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world);
 void free_sym(SymPlan& p);
+// What the reduction launch does besides summing the partial planes (unsharded engines with one panel only):
+enum SymTailMode {
+    kSymTailNone = 0,       // accelerations only
+    kSymTailKick,           // + second half-kick (device-resolved contacts follow in their own launches)
+    kSymTailClose,          // + second half-kick, history append, step bookkeeping
+    kSymTailCloseNext       // + the first half-kick and drift of the next step (multi-step graphs)
+};
+bool sym_tail_applicable(const SymPlan& p);
 cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const SymPlan& p, bool detect,
-                             cudaStream_t st, int* launches);
+                             cudaStream_t st, int* launches, int tail_mode = kSymTailNone);
 bool sym_uniform(const SymPlan& p, const StepParams& sp);
 const char* sym_kernel_name(int ti, bool detect, bool uniform);
 
