@@ -438,15 +438,18 @@ void free_sym(SymPlan& p) {
 cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world) {
     free_sym(p);
     const char* env_ti = getenv("ORBITAL_B200_SYM_TI");
-    // I-blocks (128*TI bodies) must be tile aligned (a multiple or a divisor of the 256-body tile), otherwise a
+    // I-blocks (128*TI bodies) must be tile aligned (a multiple or a divisor of the source tile), otherwise a
     // tile straddling two I-blocks would be treated one-sided by the lower block and its other bodies would miss
-    // those pairs: TI in {1, 2, 4, 6, 8}.  Measured on B200 (profiles/r1_sweep_n.txt): TI=8 is fastest from
-    // N=8192 up (N=262144: TI=8 39.4 ms, TI=4 41.5 ms; N=8192: 0.076 vs 0.115 ms for TI=2), TI=2 at 4096,
-    // TI=1 below.
+    // those pairs: TI in {1, 2, 4, 6, 8} with tiles of 64 / 128 / 256 bodies.  Geometry from the whole-step sweep on
+    // B200 (profiles/r2_sweep_step_uniform.txt, us per step for the best / runner-up): N=1,024 13.4 (TI 1, tile 64),
+    // 2,048 15.4 (TI 2, tile 64), 4,096 24.2 (TI 4, tile 128; TI 2 / tile 64: 35.4), 8,192 58.5 (TI 8, tile 256;
+    // tile 64: 66.8), 16,384 197, 32,768 694, 65,536 2,609 (TI 8, tile 256).  Small systems want many small items
+    // (one CTA per SM leaves a warp alone on its scheduler); from ~8k bodies up the larger tile wins because every
+    // chunk adds a P_i plane to the reduction.
     int ti = 8;
-    if (n < 8 * 1024) ti = 4;
-    if (n < 6 * 1024) ti = 2;
-    if (n < 3 * 1024) ti = 1;
+    if (n <= 6144) ti = 4;
+    if (n <= 3072) ti = 2;
+    if (n <= 1536) ti = 1;
     if (env_ti) {
         const int v = atoi(env_ti);
         if (v == 1 || v == 2 || v == 4 || v == 6 || v == 8) ti = v;
@@ -457,10 +460,8 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
     p.world = world;
     p.B = (long long)kFastThreads * ti;
     p.nb_I = (int)((n + p.B - 1) / p.B);
-    // Source-tile size.  An item is (I-block, chunk of tiles); with 256-body tiles a mid-size system has too few items
-    // to balance over 148 x 2 CTA slots (N = 16,384, TI = 8: 544 items of ~85 us each for a 155 us pass), so small
-    // systems use finer tiles.  The reduction reads one P_i plane per chunk, which bounds how fine is useful.
-    p.tile = n <= 32768 ? 64 : (n <= 65536 ? 128 : kTile);
+    // Source-tile size: see the sweep above.
+    p.tile = n <= 3072 ? 64 : (n <= 6144 ? 128 : kTile);
     {
         const char* env_tile = getenv("ORBITAL_B200_SYM_TILE");
         if (env_tile) {
