@@ -81,6 +81,10 @@ struct orb_engine {
     int kernels_per_step = 0;
     long long launches = 0;
     bool have_state = false;
+    // the device-side step / contact counters run on between orb_step calls: the host keeps the values it has
+    // already reported and only resets the control block after a halted step (one launch less per call)
+    bool ctl_needs_reset = false;
+    long long base_steps = 0, base_contacts = 0;
 };
 
 namespace {
@@ -472,6 +476,8 @@ int orb_set_history(orb_engine* e, int64_t capacity) {
     }
     ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 1, 0);
     CU(cudaGetLastError());
+    e->base_steps = e->base_contacts = 0;
+    e->ctl_needs_reset = false;
     return ORB_OK;
 }
 
@@ -576,6 +582,8 @@ int orb_accel(orb_engine* e) {
     if (!e->have_state) return fail(ORB_ERR_INVALID, "orb_accel before orb_upload");
     ctl_reset_kernel<<<1, 1, 0, e->stream>>>(e->s.ctl, 0, 1);     // a new force build: any stashed U is stale
     CU(cudaGetLastError());
+    e->base_steps = e->base_contacts = 0;
+    e->ctl_needs_reset = false;
     int launches = 1;
     int rc = enqueue_force(e, false, &launches);
     e->launches += launches;
@@ -588,14 +596,18 @@ int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_over
     if (nsteps < 0) return fail(ORB_ERR_INVALID, "negative nsteps");
     if (e->sharded) return fail(ORB_ERR_INVALID, "sharded engines step with orb_step_begin/orb_step_finish");
     cudaStream_t st = e->stream;
-    ctl_reset_kernel<<<1, 1, 0, st>>>(e->s.ctl, 0, 0);
-    CU(cudaGetLastError());
-    ++e->launches;
+    if (e->ctl_needs_reset) {                 // the previous call ended in a halted step
+        ctl_reset_kernel<<<1, 1, 0, st>>>(e->s.ctl, 0, 0);
+        CU(cudaGetLastError());
+        ++e->launches;
+        e->base_steps = e->base_contacts = 0;
+        e->ctl_needs_reset = false;
+    }
     if (nsteps > 0) {
         if (use_tiny(e)) {
             CU(launch_tiny_steps(e->s, e->p, nsteps, e->detect, st));
             ++e->launches;
-        } else if (nsteps == 1 || st == cudaStreamLegacy || st == nullptr) {
+        } else if (st == cudaStreamLegacy || st == nullptr) {
             // (stream capture is not available on the legacy default stream)
             for (int64_t k = 0; k < nsteps; ++k) {
                 int launches = 0;
@@ -624,9 +636,13 @@ int orb_step(orb_engine* e, int64_t nsteps, int64_t* steps_done, int64_t* n_over
     }
     CU(cudaMemcpyAsync(e->h_ctl, e->s.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (steps_done) *steps_done = e->h_ctl->steps_done;
+    if (steps_done) *steps_done = e->h_ctl->steps_done - e->base_steps;
     if (n_overlaps)
-        *n_overlaps = e->p.device_contacts ? (int64_t)e->h_ctl->contacts_total : (int64_t)e->h_ctl->overlap_count;
+        *n_overlaps = e->p.device_contacts ? (int64_t)(e->h_ctl->contacts_total - e->base_contacts)
+                                           : (int64_t)e->h_ctl->overlap_count;
+    e->base_steps = e->h_ctl->steps_done;
+    e->base_contacts = e->h_ctl->contacts_total;
+    if (e->h_ctl->halted) e->ctl_needs_reset = true;
     return ORB_OK;
 }
 

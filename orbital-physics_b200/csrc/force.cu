@@ -544,6 +544,133 @@ __global__ void __launch_bounds__(32) faithful_rows_kernel(const double4* __rest
     }
 }
 
+// Pass 2, producer / consumer form (default).  The ordered sum is a chain of N dependent additions per target and
+// component -- 8 cycles each, 17 us at N = 4,096, and nothing can shorten it -- so the kernel is built to make that
+// chain the ONLY thing its warp does: a CTA owns 32 targets (lane = target); four producer warps finish the terms
+// ((G m_j) inv_r3) (r_j - r_i) of 8 sources each per 32-source tile (7 FP64 per term, unordered, embarrassingly
+// parallel) into a shared-memory ring, and one consumer warp adds them in ascending source order: 3 LDS + 3 DADD
+// per source.  The matrix slabs and their source bodies arrive through a bulk-TMA ring as before.  One warp per
+// 32 targets doing everything (faithful_rows_kernel) ran the FP64 pipe at 14 %: 76 us at N = 4,096.
+constexpr int kR2Prod = 4;                       // producer warps
+constexpr int kR2TStages = 3;                    // term ring: 3 x [3][32 sources][32 targets] doubles (24 KiB each)
+constexpr int kR2MStages = 4;                    // matrix-slab ring: 4 x (8 KiB slab + 1 KiB of source bodies)
+constexpr int kR2TermBytes = 3 * 32 * 32 * 8;
+constexpr int kR2Smem = kR2TStages * kR2TermBytes + kR2MStages * (8192 + 1024) + 256;
+
+template <bool FUSE_TAIL>
+__global__ void __launch_bounds__(32 * (1 + kR2Prod)) faithful_rows2_kernel(const double4* __restrict__ pos4,
+                                                                           const double* __restrict__ invr3, double* acc,
+                                                                           long long n, long long n_rows, double G,
+                                                                           Ctl* ctl, const RowsTail tail) {
+    if (ctl->halted) return;
+    extern __shared__ __align__(128) unsigned char rows_smem[];
+    double (*terms)[3][32][32] = reinterpret_cast<double (*)[3][32][32]>(rows_smem);
+    double (*mt)[32 * 32] = reinterpret_cast<double (*)[32 * 32]>(rows_smem + kR2TStages * kR2TermBytes);
+    double4 (*praw)[32] = reinterpret_cast<double4 (*)[32]>(rows_smem + kR2TStages * kR2TermBytes + kR2MStages * 8192);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rows_smem + kR2TStages * kR2TermBytes + kR2MStages * (8192 + 1024));
+    uint64_t* mfull = bars;                       // TMA landed                      (1 arrival + tx bytes)
+    uint64_t* mempty = bars + kR2MStages;         // producers are done with a slab  (kR2Prod arrivals)
+    uint64_t* tfull = bars + 2 * kR2MStages;      // producers filled a term stage   (kR2Prod arrivals)
+    uint64_t* tempty = tfull + kR2TStages;        // consumer drained a term stage   (1 arrival)
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;            // 0: consumer, 1..kR2Prod: producers
+    const long long i = blockIdx.x * 32LL + lane;
+    const double4 me = pos4[min(i, n - 1)];
+    const double* blk = invr3 + (long long)blockIdx.x * n_rows * 32;
+    const int ntile = (int)(n_rows / 32);
+    auto issue = [&](int t) {
+        const int st = t % kR2MStages;
+        const uint32_t pbytes = (uint32_t)min(32LL, n - 32LL * t) * 32u;
+        mbar_expect_tx(&mfull[st], 8192u + pbytes);
+        tma_load_1d(mt[st], blk + (long long)t * 1024, 8192u, &mfull[st]);
+        tma_load_1d(praw[st], pos4 + 32LL * t, pbytes, &mfull[st]);
+    };
+    if (threadIdx.x == 32) {                      // producer 0, lane 0 owns the TMA ring
+        for (int s = 0; s < kR2MStages; ++s) { mbar_init(&mfull[s], 1); mbar_init(&mempty[s], kR2Prod); }
+        for (int s = 0; s < kR2TStages; ++s) { mbar_init(&tfull[s], kR2Prod); mbar_init(&tempty[s], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 32)
+        for (int t = 0; t < min(kR2MStages, ntile); ++t) issue(t);
+
+    if (warp > 0) {
+        // ---------------- producers: terms of sources [8 p, 8 p + 8) of every tile, lane = target
+        const int p = warp - 1;
+        for (int t = 0; t < ntile; ++t) {
+            const int ms = t % kR2MStages, ts = t % kR2TStages;
+            if (p == 0 && lane == 0 && t >= 1 && t - 1 + kR2MStages < ntile) {
+                // refill the slab freed one tile ago: never waits on this tile's stragglers
+                mbar_wait(&mempty[(t - 1) % kR2MStages], (uint32_t)(((t - 1) / kR2MStages) & 1));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(t - 1 + kR2MStages);
+            }
+            mbar_wait(&mfull[ms], (uint32_t)((t / kR2MStages) & 1));
+            if (t >= kR2TStages) mbar_wait(&tempty[ts], (uint32_t)(((t / kR2TStages) + 1) & 1));
+            const double* m = mt[ms] + lane;
+#pragma unroll
+            for (int kk = 0; kk < 32 / kR2Prod; ++kk) {
+                const int k = p * (32 / kR2Prod) + kk;
+                const bool ok = 32LL * t + k < n;                               // rows past the end hold inv_r3 = 0
+                const double4 q = ok ? praw[ms][k] : make_double4(0.0, 0.0, 0.0, 0.0);   // broadcast
+                const double s = __dmul_rn(__dmul_rn(G, q.w), m[k * 32]);       // (G m_j) inv_r3     :151
+                terms[ts][0][k][lane] = __dmul_rn(s, __dsub_rn(q.x, me.x));      // s * rij            :154
+                terms[ts][1][k][lane] = __dmul_rn(s, __dsub_rn(q.y, me.y));
+                terms[ts][2][k][lane] = __dmul_rn(s, __dsub_rn(q.z, me.z));
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tfull[ts]);
+                mbar_arrive(&mempty[ms]);
+            }
+        }
+        return;
+    }
+    // ---------------- consumer: the ordered sums (physics.py:154 accumulates in loop order)
+    double bx = 0.0, by = 0.0, bz = 0.0;                        // physics.py:132
+    for (int t = 0; t < ntile; ++t) {
+        const int ts = t % kR2TStages;
+        mbar_wait(&tfull[ts], (uint32_t)((t / kR2TStages) & 1));
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            bx = __dadd_rn(bx, terms[ts][0][k][lane]);
+            by = __dadd_rn(by, terms[ts][1][k][lane]);
+            bz = __dadd_rn(bz, terms[ts][2][k][lane]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ts]);
+    }
+    if (i < n) {
+        acc[i] = bx;
+        acc[i + n] = by;
+        acc[i + 2 * n] = bz;
+    }
+    if (FUSE_TAIL) {
+        if (i < n) {
+            const bool f32 = tail.vf32[i] != 0;
+            tail.vel[i] = kick_faithful(tail.vel[i], tail.h, bx, f32);
+            tail.vel[i + n] = kick_faithful(tail.vel[i + n], tail.h, by, f32);
+            tail.vel[i + 2 * n] = kick_faithful(tail.vel[i + 2 * n], tail.h, bz, f32);
+            if (tail.hist_cap > 0 && ctl->overlap_count == 0) {            // a halting step appends on the host
+                double* row = tail.hist + ((ctl->hist_count % tail.hist_cap) * n + i) * 3;
+                row[0] = me.x; row[1] = me.y; row[2] = me.z;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(&ctl->rows_done, 1u) == gridDim.x - 1) {         // every CTA has read hist_count by now
+                ctl->rows_done = 0;
+                ctl->steps_done += 1;
+                if (ctl->overlap_count > 0)
+                    ctl->halted = 1;
+                else if (tail.hist_cap > 0)
+                    ctl->hist_count += 1;
+            }
+        }
+    }
+}
+
 bool faithful_pairs_applicable(long long n, bool sharded) {
     const char* env = getenv("ORBITAL_B200_FAITHFUL_PAIRS");     // "0": always the one-pass kernel (cross-check)
     if (env && env[0] == '0') return false;
@@ -598,6 +725,24 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
             cudaFuncSetAttribute(faithful_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
         }
         const RowsTail tail = {s.vel, s.vf32, s.hist, s.hist_cap, p.h};
+        static const bool one_warp_rows = [] {                   // "1": the one-warp-per-block pass 2 (cross-check)
+            const char* env = getenv("ORBITAL_B200_ROWS_ONE_WARP");
+            return env && env[0] == '1';
+        }();
+        if (!one_warp_rows) {
+            static DeviceOnce rows2_attr;
+            if (rows2_attr.first()) {
+                cudaFuncSetAttribute(faithful_rows2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2Smem);
+                cudaFuncSetAttribute(faithful_rows2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2Smem);
+            }
+            if (fuse_tail)
+                faithful_rows2_kernel<true><<<nb, 32 * (1 + kR2Prod), kR2Smem, st>>>(s.pos4, s.invr3, s.acc, s.n,
+                                                                                   s.invr3_ld, p.G, s.ctl, tail);
+            else
+                faithful_rows2_kernel<false><<<nb, 32 * (1 + kR2Prod), kR2Smem, st>>>(s.pos4, s.invr3, s.acc, s.n,
+                                                                                    s.invr3_ld, p.G, s.ctl, tail);
+            return;
+        }
         if (fuse_tail)
             faithful_rows_kernel<true><<<nb, 32, kRowSmem, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl,
                                                                 tail);
