@@ -549,8 +549,13 @@ __global__ void __launch_bounds__(32) faithful_rows_kernel(const double4* __rest
 // chain the ONLY thing its warp does: a CTA owns 32 targets (lane = target); four producer warps finish the terms
 // ((G m_j) inv_r3) (r_j - r_i) of 8 sources each per 32-source tile (7 FP64 per term, unordered, embarrassingly
 // parallel) into a shared-memory ring, and one consumer warp adds them in ascending source order: 3 LDS + 3 DADD
-// per source.  The matrix slabs and their source bodies arrive through a bulk-TMA ring as before.  One warp per
-// 32 targets doing everything (faithful_rows_kernel) ran the FP64 pipe at 14 %: 76 us at N = 4,096.
+// per source.  The matrix slabs and their source bodies arrive through a bulk-TMA ring as before.
+// Measured (profiles/r2_sweep_faithful_step*.txt, whole step): N = 1,024 27.8 us (one warp per 32 targets doing
+// everything: 30.8), 2,048 49.8 (55.3), 4,096 111 (119); from 8,192 up the one-warp kernel wins (298 vs 408 us) because
+// its small CTAs pack six to an SM while this one's 108 KiB of rings allow one -- so it serves up to 148 blocks.
+// What bounds BOTH at N = 4,096 is the 134 MB pair matrix coming back from DRAM at ~1.7 TB/s (ncu: L2 hit rate 4 %;
+// neither a 12-deep ring, nor an odd slab stride against channel aliasing, nor plain register-prefetched loads
+// instead of TMA moved it): the ordered chain itself is 17 us.
 constexpr int kR2Prod = 4;                       // producer warps
 constexpr int kR2TStages = 3;                    // term ring: 3 x [3][32 sources][32 targets] doubles (24 KiB each)
 constexpr int kR2MStages = 4;                    // matrix-slab ring: 4 x (8 KiB slab + 1 KiB of source bodies)
@@ -608,15 +613,26 @@ __global__ void __launch_bounds__(32 * (1 + kR2Prod)) faithful_rows2_kernel(cons
             mbar_wait(&mfull[ms], (uint32_t)((t / kR2MStages) & 1));
             if (t >= kR2TStages) mbar_wait(&tempty[ts], (uint32_t)(((t / kR2TStages) + 1) & 1));
             const double* m = mt[ms] + lane;
+            constexpr int kPer = 32 / kR2Prod;
+            // all loads first: the term stores below live in the same shared array, so the compiler cannot hoist a
+            // load over them by itself (ncu: every source stalled on its own LDS)
+            double4 q[kPer];
+            double inv[kPer];
 #pragma unroll
-            for (int kk = 0; kk < 32 / kR2Prod; ++kk) {
-                const int k = p * (32 / kR2Prod) + kk;
-                const bool ok = 32LL * t + k < n;                               // rows past the end hold inv_r3 = 0
-                const double4 q = ok ? praw[ms][k] : make_double4(0.0, 0.0, 0.0, 0.0);   // broadcast
-                const double s = __dmul_rn(__dmul_rn(G, q.w), m[k * 32]);       // (G m_j) inv_r3     :151
-                terms[ts][0][k][lane] = __dmul_rn(s, __dsub_rn(q.x, me.x));      // s * rij            :154
-                terms[ts][1][k][lane] = __dmul_rn(s, __dsub_rn(q.y, me.y));
-                terms[ts][2][k][lane] = __dmul_rn(s, __dsub_rn(q.z, me.z));
+            for (int kk = 0; kk < kPer; ++kk) {
+                const int k = p * kPer + kk;
+                q[kk] = praw[ms][k];                                            // broadcast
+                inv[kk] = m[k * 32];
+            }
+            const int valid = (int)min(32LL, n - 32LL * t);                     // sources past the end: zero bodies
+#pragma unroll
+            for (int kk = 0; kk < kPer; ++kk) {
+                const int k = p * kPer + kk;
+                if (k >= valid) q[kk] = make_double4(0.0, 0.0, 0.0, 0.0);       // (their inv_r3 rows are zero too)
+                const double s = __dmul_rn(__dmul_rn(G, q[kk].w), inv[kk]);     // (G m_j) inv_r3     :151
+                terms[ts][0][k][lane] = __dmul_rn(s, __dsub_rn(q[kk].x, me.x));  // s * rij            :154
+                terms[ts][1][k][lane] = __dmul_rn(s, __dsub_rn(q[kk].y, me.y));
+                terms[ts][2][k][lane] = __dmul_rn(s, __dsub_rn(q[kk].z, me.z));
             }
             __syncwarp();
             if (lane == 0) {
@@ -729,7 +745,7 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
             const char* env = getenv("ORBITAL_B200_ROWS_ONE_WARP");
             return env && env[0] == '1';
         }();
-        if (!one_warp_rows) {
+        if (!one_warp_rows && nb <= 148) {
             static DeviceOnce rows2_attr;
             if (rows2_attr.first()) {
                 cudaFuncSetAttribute(faithful_rows2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2Smem);
