@@ -1,11 +1,13 @@
-// ensemble.cu -- batched ensemble of independent small systems, one CTA per system (sm_100a).
+// ensemble.cu -- batched ensemble of independent small systems (sm_100a): one warp per system (bit-exact) or
+// nbody/2 lanes per system, 64/nbody systems per warp (fast).
 //
 // Equivalent to `nsys` separate reference SimulationEngine instances
 // (core/engine.py:19-46,65-97; force: core/physics.py:125-159) stepped in
-// lockstep, without collision handling. State is SoA [nsys][nbody] fp64:
-// x y z vx vy vz ax ay az (read+write) and m (read): 152 B per body-step when a
-// launch covers one step (HBM-bound mode); with `nsteps` fused in one launch the
-// state stays in registers and the kernel is FP64-bound.
+// lockstep, including -- when radii are given -- the contact sweep each engine runs after its step
+// (engine.py:85 -> physics.py:510-535) and per-body velocity dtypes.  State is SoA [nsys][nbody] fp64.
+// One step per launch (HBM-bound): x, u (half-kicked velocity), m in and x, u out = 104 B per body-step
+// (see the first / last note below); with `nsteps` fused in one launch the state stays in registers and the
+// kernel is FP64-bound.
 //
 //   FAITHFUL: lane i owns body i and accumulates j ascending with the reference's
 //             rounding sequence (bit-exact with the reference engine).

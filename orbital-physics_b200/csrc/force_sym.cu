@@ -279,10 +279,16 @@ _Pragma(ORB_STR(unroll SYM_UNROLL))
     }
 }
 
-// G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{owned I-blocks of this panel before x} P_j[slot][x] ), fixed order
+// Every element x is summed by kRedSplit threads (a quarter of the planes each, combined in fixed order): at
+// N = 4,096 one thread per element meant 16 CTAs walking ~75 dependent-latency loads each -- 11 us, more than half
+// of the force kernel it follows.
+constexpr int kRedSplit = 4;
+constexpr int kRedX = 256 / kRedSplit;           // elements per CTA
+
+// share `sub` of  sum_{chunks of x's I-block} P_i[chunk][x] + sum_{owned I-blocks of this panel before x} P_j[slot][x]
 __device__ __forceinline__ void sym_reduce_row(const double* __restrict__ Pi, const double* __restrict__ Pj, long long n,
                                                long long B, int tile, int chunk_tiles, int n_chunks, int rank, int world,
-                                               int ka, int kb, double G, long long x, double (&out)[3]) {
+                                               int ka, int kb, int sub, long long x, double (&out)[3]) {
     const long long X = x / B;
     const long long T = x / tile;
     double s[3] = {0.0, 0.0, 0.0};
@@ -290,7 +296,7 @@ __device__ __forceinline__ void sym_reduce_row(const double* __restrict__ Pi, co
         const long long kx = (X - rank) / world;
         if (kx >= ka && kx < kb) {
             const int c_first = (int)(((X * B) / tile) / chunk_tiles);
-            for (int c = c_first; c < n_chunks; ++c) {
+            for (int c = c_first + sub; c < n_chunks; c += kRedSplit) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s[k] += Pi[((long long)c * 3 + k) * n + x];
             }
@@ -300,12 +306,12 @@ __device__ __forceinline__ void sym_reduce_row(const double* __restrict__ Pi, co
     const long long nI = (T * tile) / B;
     long long kend = nI > rank ? (nI - rank + world - 1) / world : 0;
     if (kend > kb) kend = kb;
-    for (long long k = ka; k < kend; ++k) {
+    for (long long k = ka + sub; k < kend; k += kRedSplit) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) s[c] += Pj[((k - ka) * 3 + c) * n + x];
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out[k] = G * s[k];
+    for (int k = 0; k < 3; ++k) out[k] = s[k];
 }
 
 // The rest of the leapfrog step, riding along in the reduction (unsharded engines, one panel): a step is then
@@ -334,14 +340,31 @@ __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restric
                                                          int kb, double G, int accumulate, const Ctl* ctl,
                                                          const SymTail tail) {
     if (ctl->halted) return;
-    const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    __shared__ double part[kRedSplit - 1][3][kRedX];
+    const int xl = threadIdx.x % kRedX, sub = threadIdx.x / kRedX;
+    const long long x = blockIdx.x * (long long)kRedX + xl;
+    double a3[3] = {0.0, 0.0, 0.0};
+    if (x < n) sym_reduce_row(Pi, Pj, n, B, tile, chunk_tiles, n_chunks, rank, world, ka, kb, sub, x, a3);
+    if (sub > 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) part[sub - 1][k][xl] = a3[k];
+    }
+    __syncthreads();
+    if (sub == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double v = a3[k];
+#pragma unroll
+            for (int q = 0; q < kRedSplit - 1; ++q) v += part[q][k][xl];     // fixed order: deterministic
+            a3[k] = G * v;
+        }
+    }
+    const bool mine = sub == 0 && x < n;
     if (tail.close) {
         // every thread has read the ring cursor / overlap count before the last CTA to arrive moves them
         const long long hist_count = ctl->hist_count;
         const int overlaps = ctl->overlap_count;
-        if (x < n) {
-            double a3[3];
-            sym_reduce_row(Pi, Pj, n, B, tile, chunk_tiles, n_chunks, rank, world, ka, kb, G, x, a3);
+        if (mine) {
             acc[x] = a3[0]; acc[x + n] = a3[1]; acc[x + 2 * n] = a3[2];
             const bool f32 = tail.vf32[x] != 0;
             double vx = kick_faithful(tail.vel[x], tail.h, a3[0], f32);
@@ -378,9 +401,7 @@ __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restric
         }
         return;
     }
-    if (x >= n) return;
-    double a3[3];
-    sym_reduce_row(Pi, Pj, n, B, tile, chunk_tiles, n_chunks, rank, world, ka, kb, G, x, a3);
+    if (!mine) return;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double v = accumulate ? acc[x + k * n] + a3[k] : a3[k];
@@ -590,7 +611,7 @@ cudaError_t launch_force_sym(const DeviceState& s, const StepParams& sp, const S
         }
 #undef ORB_SYM_CASE
         if (e != cudaSuccess) return e;
-        const int grid = (int)((s.n + 255) / 256);
+        const int grid = (int)((s.n + kRedX - 1) / kRedX);
         reduce_sym_kernel<<<grid, 256, 0, st>>>(p.Pi, p.Pj, s.acc, s.n, p.B, p.tile, p.chunk_tiles, p.n_chunks, p.rank, p.world,
                                                 pan.ka, pan.kb, scale, first ? 0 : 1, s.ctl, tail);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
