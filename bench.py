@@ -272,7 +272,7 @@ def ensemble_measure(device, torch, nsys=65536, nbody=16, steps=200, world=1, ra
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(fused):
-        ens.step(20, fused=fused)
+        ens.step(steps, fused=fused)          # warm-up on the same path (small batches take the time-sliced kernel)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
