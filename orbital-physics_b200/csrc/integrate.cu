@@ -404,35 +404,38 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
         const int j = p - i * (2 * n - i - 1) / 2 + i + 1;
         plist[p] = (unsigned short)((i << 8) | j);
     }
-    const bool active = tid < n;
-    double x = 0, y = 0, z = 0, gm = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0;
+    // Integrator and row sums: one thread per (body, COMPONENT), the three components of a body in three different
+    // warps.  The step is one dependent chain (kick -> drift -> pairs -> ordered row sum -> kick); with a thread per
+    // body, one warp issued ~190 instructions of it per step, now each of three warps issues a third (ncu, N = 15:
+    // 373 instructions per step on warp 0, issue slots 12 % busy, everything stalled on the previous result).
+    const int S = n <= 32 ? 32 : 64;                        // threads per component plane
+    const int comp = tid / S, body = tid - comp * S;
+    const bool active = comp < 3 && body < n;
+    const int plane = n * stride;
+    double q = 0, v = 0, a = 0, gm = 0;                     // this thread's component of position / velocity / acc
     bool f32 = false;
     if (active) {
-        const double4 p = pos4[tid];
-        x = p.x; y = p.y; z = p.z;
+        const double4 p = pos4[body];
+        q = comp == 0 ? p.x : (comp == 1 ? p.y : p.z);
         gm = __dmul_rn(G, p.w);                              // G * m (physics.py:151-152)
-        vx = vel[tid]; vy = vel[tid + n]; vz = vel[tid + 2 * n];
-        ax = acc[tid]; ay = acc[tid + n]; az = acc[tid + 2 * n];
-        f32 = vf32[tid] != 0;
-        sr[tid] = radius[tid];
-        T[tid * stride + tid] = 0.0;                         // diagonal of the three term planes: +0.0
-        T[n * stride + tid * stride + tid] = 0.0;
-        T[2 * n * stride + tid * stride + tid] = 0.0;
+        v = vel[body + comp * n];
+        a = acc[body + comp * n];
+        f32 = vf32[body] != 0;
+        if (comp == 0) sr[body] = radius[body];
+        T[comp * plane + body * stride + body] = 0.0;        // diagonal of the three term planes: +0.0
     }
+    double* spq = reinterpret_cast<double*>(sp + body) + comp;       // this thread's slot of sp[body]
     __syncthreads();
     const int first_pair = tid < npairs ? plist[tid] : 0;   // most systems: at most one pair per lane
     const long long hist0 = ctl->hist_count;
     long long slot = hist_cap > 0 ? hist0 % hist_cap : 0;    // ring cursor, advanced without a 64-bit modulo per step
     long long done = 0;
+    if (active && comp == 0) sp[body].w = gm;
     for (long long s = 0; s < nsteps; ++s) {
         if (active) {
-            vx = kick_faithful(vx, h, ax, f32);                      // engine.py:69-70
-            vy = kick_faithful(vy, h, ay, f32);
-            vz = kick_faithful(vz, h, az, f32);
-            x = drift_faithful(x, vx, dt, dt32, f32);                // engine.py:73-75
-            y = drift_faithful(y, vy, dt, dt32, f32);
-            z = drift_faithful(z, vz, dt, dt32, f32);
-            sp[tid] = make_double4(x, y, z, gm);
+            v = kick_faithful(v, h, a, f32);                         // engine.py:69-70
+            q = drift_faithful(q, v, dt, dt32, f32);                 // engine.py:73-75
+            *spq = q;
         }
         __syncthreads();
         for (int p = tid; p < npairs; p += blockDim.x) {            // physics.py:136-155, one pair per lane
@@ -449,7 +452,6 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             const double sj = __dmul_rn(pi.w, inv_r3);               // (G mi) inv_r3          :152 (sign applied below)
             double* Ti = T + i * stride + j;
             double* Tj = T + j * stride + i;
-            const int plane = n * stride;
             Ti[0] = __dmul_rn(si, dx); Ti[plane] = __dmul_rn(si, dy); Ti[2 * plane] = __dmul_rn(si, dz);
             Tj[0] = -__dmul_rn(sj, dx); Tj[plane] = -__dmul_rn(sj, dy); Tj[2 * plane] = -__dmul_rn(sj, dz);
             if (touching) {
@@ -462,30 +464,23 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
         const int hits = DETECT ? hitflag[s & 1] : 0;
         if (DETECT && tid == 0) hitflag[(s + 1) & 1] = 0;
         if (active) {
-            const double* row = T + tid * stride;
-            const int plane = n * stride;
-            double bx = 0.0, by = 0.0, bz = 0.0;                     // physics.py:132
-            // ascending j.  The diagonal entry holds +0.0 (set once below): x + 0.0 == x bit for bit because a
-            // running sum that starts at +0.0 can never be -0.0, so the self pair is "skipped" without a branch
-            // and the shared-memory loads pipeline freely.
+            const double* row = T + comp * plane + body * stride;
+            double b = 0.0;                                          // physics.py:132
+            // ascending j.  The diagonal entry holds +0.0: x + 0.0 == x bit for bit because a running sum that
+            // starts at +0.0 can never be -0.0, so the self pair is "skipped" without a branch and the
+            // shared-memory loads pipeline freely.
 #pragma unroll 8
-            for (int j = 0; j < n; ++j) {
-                bx = __dadd_rn(bx, row[j]);
-                by = __dadd_rn(by, row[plane + j]);
-                bz = __dadd_rn(bz, row[2 * plane + j]);
-            }
-            ax = bx; ay = by; az = bz;
-            vx = kick_faithful(vx, h, ax, f32);                      // engine.py:81-82
-            vy = kick_faithful(vy, h, ay, f32);
-            vz = kick_faithful(vz, h, az, f32);
+            for (int j = 0; j < n; ++j) b = __dadd_rn(b, row[j]);
+            a = b;
+            v = kick_faithful(v, h, a, f32);                         // engine.py:81-82
         }
         ++done;
         if (hits) {
             if (!device_contacts) break;                             // the host resolves and resumes
             // engine.py:85: contacts after the second half-kick, resolved here in the reference's order
             if (active) {
-                pos4[tid] = make_double4(x, y, z, pos4[tid].w);
-                vel[tid] = vx; vel[tid + n] = vy; vel[tid + 2 * n] = vz;
+                reinterpret_cast<double*>(pos4 + body)[comp] = q;
+                vel[body + comp * n] = v;
             }
             __threadfence_block();
             __syncthreads();
@@ -496,26 +491,22 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             }
             const int nh = resolve_contacts_block(pos4, vel, n, radius, vf32, restitution, ctl, pairs, cscratch);
             if (active) {
-                const double4 p = pos4[tid];
-                x = p.x; y = p.y; z = p.z;
-                vx = vel[tid]; vy = vel[tid + n]; vz = vel[tid + 2 * n];
+                q = reinterpret_cast<const double*>(pos4 + body)[comp];
+                v = vel[body + comp * n];
             }
-            if (tid == 0) { ctl->contacts_total += nh; ctl->overlap_count = 0; }
+            if (tid == 0) { ctl->contacts_total += nh; ctl->overlap_count = 0; ctl->overlap_overflow = 0; }
             __syncthreads();
         } else if (u_set) {
             if (tid == 0) ctl->u_valid = 0;
             u_set = false;
         }
-        if (active && hist_cap > 0) {                                // engine.py:88-92
-            double* hrow = hist + (slot * n + tid) * 3;
-            hrow[0] = x; hrow[1] = y; hrow[2] = z;
-        }
+        if (active && hist_cap > 0) hist[(slot * n + body) * 3 + comp] = q;   // engine.py:88-92
         if (++slot >= hist_cap) slot = 0;
     }
     if (active) {
-        pos4[tid] = make_double4(x, y, z, pos4[tid].w);
-        vel[tid] = vx; vel[tid + n] = vy; vel[tid + 2 * n] = vz;
-        acc[tid] = ax; acc[tid + n] = ay; acc[tid + 2 * n] = az;
+        reinterpret_cast<double*>(pos4 + body)[comp] = q;
+        vel[body + comp * n] = v;
+        acc[body + comp * n] = a;
     }
     if (tid == 0) {
         ctl->steps_done += done;
@@ -530,8 +521,8 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
 
 static int micro_block(int n) {
     const int npairs = n * (n - 1) / 2;
-    const int want = std::max(n, npairs);                   // one pair per lane if it fits
-    return std::max(32, std::min(256, ((want + 31) / 32) * 32));
+    const int want = std::max(3 * (n <= 32 ? 32 : 64), npairs);     // a thread per (body, component); a pair per lane
+    return std::max(96, std::min(256, ((want + 31) / 32) * 32));
 }
 
 static size_t micro_smem(int n) {
