@@ -6,7 +6,7 @@ slab of ceil(N / world) bodies.  One leapfrog step (reference core/engine.py:65-
     orb_step_begin   half-kick + drift of the local slab                       (rank-local)
     all_gather       the packed {x,y,z,m} slabs, in place                      (32 B x N in total)
     orb_step_force   force pass with the overlap test of engine.py:85 fused in (rank-local)
-    [all_reduce      3 x N accelerations, pair-symmetric fast kernel only]     (24 B x N)
+    [reduce_scatter  3 x N partial accelerations, pair-symmetric kernel only]  (24 B x N in, each rank keeps its slab)
     orb_step_kick    second half-kick of the local slab                        (rank-local)
     [contacts        only in a step where some rank flagged a pair: all-gather the velocities and the pair
                      lists; every rank then replays the reference's sequential sweep (physics.py:510-535)
@@ -16,7 +16,7 @@ slab of ceil(N / world) bodies.  One leapfrog step (reference core/engine.py:65-
 Bit-exact mode: every rank evaluates its own targets against all sources; a target's source order does
 not depend on the partition, so the result is bit-identical to one GPU.  Fast mode: the pair-symmetric
 kernel evaluates every unordered pair once, so each rank takes a cyclic share of the pair blocks and
-produces a partial acceleration of all N bodies, summed by the all-reduce.
+produces a partial acceleration of all N bodies; a reduce-scatter gives every rank the total for its slab.
 
 Two communicators carry the same protocol:
 
@@ -82,6 +82,18 @@ class DistComm:
     def all_reduce_sum(self, bufs):
         self.dist.all_reduce(bufs[0], group=self.group)
 
+    def reduce_scatter_rows(self, bufs, per):
+        """bufs[0]: [rows, world * per] partial sums; every rank ends up with the total of ITS columns
+        [rank * per, (rank + 1) * per) in place (NCCL's in-place reduce-scatter) -- half the traffic of an all-reduce,
+        and all the second half-kick needs."""
+        t = bufs[0]
+        if self.dist.get_backend(self.group) == "gloo":      # the CPU test backend has no reduce-scatter
+            self.dist.all_reduce(t, group=self.group)
+            return
+        for c in range(t.shape[0]):
+            row = t[c]
+            self.dist.reduce_scatter_tensor(row[self.rank * per:(self.rank + 1) * per], row, group=self.group)
+
     def all_gather_host(self, items):
         """items[0]: any picklable object of this rank -> list over ranks."""
         out = [None] * self.world
@@ -115,6 +127,13 @@ class LocalComm:
             total += b.to(total.device, non_blocking=True)
         for b in bufs:
             b.copy_(total, non_blocking=True)
+
+    def reduce_scatter_rows(self, bufs, per):
+        total = bufs[0].clone()
+        for b in bufs[1:]:                      # fixed rank order: deterministic
+            total += b.to(total.device, non_blocking=True)
+        for r, b in enumerate(bufs):
+            b[:, r * per:(r + 1) * per].copy_(total[:, r * per:(r + 1) * per], non_blocking=True)
 
     def all_gather_host(self, items):
         return list(items)
@@ -261,9 +280,16 @@ class ShardedSystem:
             self._timed("gather", lambda: self.comm.all_gather_rows(self._pos4, self.per))
 
     def _reduce_acc(self):
-        if self._partial:
+        """Sum the partial accelerations of the pair-symmetric kernel.  Equal slabs: reduce-scatter, every rank gets
+        the total for its own slab only (what its half-kick reads); ragged slabs: all-reduce."""
+        if self._partial and self.n == self.per * self.world:
+            self._timed("reduce", lambda: self.comm.reduce_scatter_rows(self._acc, self.per))
+            self._acc_full = False
+        elif self._partial:
             self._timed("reduce", lambda: self.comm.all_reduce_sum(self._acc))
-        self._acc_full = self._partial or self.world == 1
+            self._acc_full = True
+        else:
+            self._acc_full = self.world == 1
 
     def _force_pass(self):
         for d in self.devs:
