@@ -69,7 +69,7 @@ def workload(args):
     n = args.n_bodies or (262144 if args.gpus == 1 else 2097152)
     name = (f"Plummer sphere N={n} all-pairs force + leapfrog step"
             + ("" if args.gpus == 1 else f", every unordered pair once, pair blocks owned cyclically by {args.gpus} ranks, "
-                                         "all-gather 32 B x N + reduce-scatter 24 B x N per step (NCCL)"))
+                                         "all-gather 32 B x N + reduce-scatter (all-reduce below 1M bodies) 24 B x N per step (NCCL)"))
     return n, name
 
 
@@ -437,7 +437,7 @@ def timed_sharded(torch, dist, sh, steps, warmup, flush, world):
         t = torch.tensor(vals, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = [float(v) for v in t]
-    return vals[0], vals[1], {"all_gather_pos4": vals[2], "reduce_scatter_acc": vals[3]}
+    return vals[0], vals[1], {"all_gather_pos4": vals[2], "reduce_acc": vals[3]}
 
 
 def run_ours(args):
@@ -674,7 +674,7 @@ def run_ours(args):
         "config": {"workload": name, "n_bodies": n, "mode": "fast", "ic": "Plummer (Aarseth-Henon-Wielen), seed=N",
                    "interactions_per_step": "N^2", "l2": "flushed between steps (256 MiB memset)",
                    "parallelism": "1 GPU" if world == 1 else
-                                  f"cyclic pair-block ownership x{world}, all-gather 32 B x N + reduce-scatter 24 B x N"},
+                                  f"cyclic pair-block ownership x{world}, all-gather 32 B x N + reduce-scatter / all-reduce 24 B x N"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity_check": parity,
     }
