@@ -199,3 +199,43 @@ def test_multi_rank_nccl_matches_single_gpu(orc, tmp_path, kind, world):
             assert np.array_equal(got[k], ref), k
         else:
             assert np.allclose(got[k], ref, rtol=1e-11, atol=0), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["coll_dense_mixed", "solar26_f32"])
+def test_engine_over_two_real_gpus_in_one_process(golden, name):
+    """SimulationEngine(devices=2): LocalComm with one handle per GPU, peer copies instead of NCCL -- bit-exact with
+    the reference's own outputs (needs 2 GPUs; tests/test_sharded_gpu.py runs the same path with both ranks on GPU 0)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from core import distributed
+    from tests.test_engine import build_engine, check_against_golden
+    g = golden(name)
+    if name.startswith("solar"):
+        g = {k: g[k] for k in g.files}
+        g["steps"] = np.array([s for s in g["steps"] if s <= 100])
+    eng = build_engine(g, devices=2)
+    assert isinstance(eng._dev, distributed.ShardedSystem) and sorted(eng._dev.comm.devices.values()) == [0, 1]
+    check_against_golden(g, eng)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_fast_sharded_over_two_real_gpus_in_one_process(orc):
+    """Pair-symmetric kernel over 2 GPUs driven by one process: all rows <= 1e-12 of the oracle, 2 steps."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from core import _native
+    from core.distributed import LocalComm, ShardedSystem
+    c, f32, vel, radius = _scenario(8192, "gathered")
+    sh = ShardedSystem.from_arrays(c["x"], c["y"], c["z"], *vel, c["m"], radius, c["dt"], c["eps"],
+                                   mode=_native.MODE_FAST, comm=LocalComm([0, 1]), vel_is_f32=f32)
+    sh.step(2)
+    st = sh.download_state()
+    ref, _ = orc.pairwise(st["x"], st["y"], st["z"], c["m"], c["eps"], 6.67430e-11, nthreads=8)
+    got = sh.download_acc().T
+    rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() <= 1e-12
+    sh.close()
