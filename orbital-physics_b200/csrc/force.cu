@@ -556,9 +556,18 @@ __global__ void __launch_bounds__(32) faithful_rows_kernel(const double4* __rest
 // What bounds BOTH at N = 4,096 is the 134 MB pair matrix coming back from DRAM at ~1.7 TB/s (ncu: L2 hit rate 4 %;
 // neither a 12-deep ring, nor an odd slab stride against channel aliasing, nor plain register-prefetched loads
 // instead of TMA moved it): the ordered chain itself is 17 us.
-constexpr int kR2Prod = 4;                       // producer warps
-constexpr int kR2TStages = 3;                    // term ring: 3 x [3][32 sources][32 targets] doubles (24 KiB each)
-constexpr int kR2MStages = 4;                    // matrix-slab ring: 4 x (8 KiB slab + 1 KiB of source bodies)
+#ifndef R2_PROD
+#define R2_PROD 4
+#endif
+#ifndef R2_TSTAGES
+#define R2_TSTAGES 3
+#endif
+#ifndef R2_MSTAGES
+#define R2_MSTAGES 4
+#endif
+constexpr int kR2Prod = R2_PROD;                 // producer warps
+constexpr int kR2TStages = R2_TSTAGES;                    // term ring: 3 x [3][32 sources][32 targets] doubles (24 KiB each)
+constexpr int kR2MStages = R2_MSTAGES;                    // matrix-slab ring: 4 x (8 KiB slab + 1 KiB of source bodies)
 constexpr int kR2TermBytes = 3 * 32 * 32 * 8;
 constexpr int kR2Smem = kR2TStages * kR2TermBytes + kR2MStages * (8192 + 1024) + 256;
 
