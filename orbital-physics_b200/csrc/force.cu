@@ -696,6 +696,115 @@ __global__ void __launch_bounds__(32 * (1 + kR2Prod)) faithful_rows2_kernel(cons
     }
 }
 
+// Pass 2, four lanes per target (default).  The ordered sum is a chain of N dependent additions per target and
+// component (8 cycles each: 17 us at N = 4,096); one warp doing everything for 32 targets has to issue 11 FP64 + 3 LDS
+// per source and is issue-bound at ~36 cycles per source, and handing finished terms from producer warps to a consumer
+// warp through shared memory (faithful_rows2_kernel) costs more in ring traffic and handshakes than it saves.  Here a
+// warp owns 8 targets; the 4 lanes of a target finish the terms of 4 consecutive sources at once (8 FP64, one warp
+// instruction each) and every lane then adds the 4 terms in source order, fetching them with shuffles -- the
+// accumulator is replicated in the 4 lanes, bit for bit.  Per source: 2 + 3 FP64 and 3 SHFL warp instructions, no
+// shared-memory stores, no cross-warp synchronisation beyond the TMA ring of matrix slabs the 4 warps of a CTA share.
+constexpr int kR4Stages = 4;
+constexpr int kR4Smem = kR4Stages * (8192 + 1024) + 128;
+
+template <bool FUSE_TAIL>
+__global__ void __launch_bounds__(128) faithful_rows4_kernel(const double4* __restrict__ pos4,
+                                                             const double* __restrict__ invr3, double* acc, long long n,
+                                                             long long n_rows, double G, Ctl* ctl, const RowsTail tail) {
+    if (ctl->halted) return;
+    extern __shared__ __align__(128) unsigned char rows_smem[];
+    double (*mt)[32 * 32] = reinterpret_cast<double (*)[32 * 32]>(rows_smem);                  // slabs of the matrix
+    double4 (*praw)[32] = reinterpret_cast<double4 (*)[32]>(rows_smem + kR4Stages * 8192);     // their source bodies
+    uint64_t* full = reinterpret_cast<uint64_t*>(rows_smem + kR4Stages * (8192 + 1024));
+    uint64_t* empty = full + kR4Stages;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane & 3;                     // which of 4 consecutive sources this lane finishes
+    const int col = warp * 8 + (lane >> 2);       // target column inside the 32-wide block
+    const int grp = lane & ~3;
+    const long long i = blockIdx.x * 32LL + col;
+    const double4 me = pos4[min(i, n - 1)];
+    const double* blk = invr3 + (long long)blockIdx.x * n_rows * 32;
+    const int ntile = (int)((n + 31) / 32);       // rows past the last body are never needed
+    auto issue = [&](int t) {
+        const int st = t % kR4Stages;
+        const uint32_t pbytes = (uint32_t)min(32LL, n - 32LL * t) * 32u;
+        mbar_expect_tx(&full[st], 8192u + pbytes);
+        tma_load_1d(mt[st], blk + (long long)t * 1024, 8192u, &full[st]);
+        tma_load_1d(praw[st], pos4 + 32LL * t, pbytes, &full[st]);
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kR4Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int t = 0; t < min(kR4Stages, ntile); ++t) issue(t);
+
+    double bx = 0.0, by = 0.0, bz = 0.0;                        // physics.py:132 (replicated in the 4 lanes)
+    for (int t = 0; t < ntile; ++t) {
+        const int st = t % kR4Stages;
+        if (threadIdx.x == 0 && t >= 1 && t - 1 + kR4Stages < ntile) {
+            // refill the slab freed one tile ago: never waits on this tile's stragglers
+            mbar_wait(&empty[(t - 1) % kR4Stages], (uint32_t)(((t - 1) / kR4Stages) & 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(t - 1 + kR4Stages);
+        }
+        mbar_wait(&full[st], (uint32_t)((t / kR4Stages) & 1));
+        const int valid = (int)min(32LL, n - 32LL * t);
+        const double* m = mt[st] + col;
+#pragma unroll
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            const int k = k0 + sub;
+            double4 q = praw[st][k];
+            if (k >= valid) q = make_double4(0.0, 0.0, 0.0, 0.0);               // past the end: a zero body, inv_r3 = 0
+            const double sc = __dmul_rn(__dmul_rn(G, q.w), m[k * 32]);          // (G m_j) inv_r3     :151
+            const double tx = __dmul_rn(sc, __dsub_rn(q.x, me.x));               // s * rij            :154
+            const double ty = __dmul_rn(sc, __dsub_rn(q.y, me.y));
+            const double tz = __dmul_rn(sc, __dsub_rn(q.z, me.z));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                                       // ascending source order
+                bx = __dadd_rn(bx, __shfl_sync(0xffffffffu, tx, grp | j));
+                by = __dadd_rn(by, __shfl_sync(0xffffffffu, ty, grp | j));
+                bz = __dadd_rn(bz, __shfl_sync(0xffffffffu, tz, grp | j));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    const bool writer = sub == 0 && i < n;
+    if (writer) {
+        acc[i] = bx;
+        acc[i + n] = by;
+        acc[i + 2 * n] = bz;
+    }
+    if (FUSE_TAIL) {
+        if (writer) {
+            const bool f32 = tail.vf32[i] != 0;
+            tail.vel[i] = kick_faithful(tail.vel[i], tail.h, bx, f32);
+            tail.vel[i + n] = kick_faithful(tail.vel[i + n], tail.h, by, f32);
+            tail.vel[i + 2 * n] = kick_faithful(tail.vel[i + 2 * n], tail.h, bz, f32);
+            if (tail.hist_cap > 0 && ctl->overlap_count == 0) {            // a halting step appends on the host
+                double* row = tail.hist + ((ctl->hist_count % tail.hist_cap) * n + i) * 3;
+                row[0] = me.x; row[1] = me.y; row[2] = me.z;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&ctl->rows_done, 1u) == gridDim.x - 1) {         // every CTA has read hist_count by now
+                ctl->rows_done = 0;
+                ctl->steps_done += 1;
+                if (ctl->overlap_count > 0)
+                    ctl->halted = 1;
+                else if (tail.hist_cap > 0)
+                    ctl->hist_count += 1;
+            }
+        }
+    }
+}
+
 bool faithful_pairs_applicable(long long n, bool sharded) {
     const char* env = getenv("ORBITAL_B200_FAITHFUL_PAIRS");     // "0": always the one-pass kernel (cross-check)
     if (env && env[0] == '0') return false;
@@ -750,11 +859,26 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
             cudaFuncSetAttribute(faithful_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
         }
         const RowsTail tail = {s.vel, s.vf32, s.hist, s.hist_cap, p.h};
-        static const bool one_warp_rows = [] {                   // "1": the one-warp-per-block pass 2 (cross-check)
-            const char* env = getenv("ORBITAL_B200_ROWS_ONE_WARP");
-            return env && env[0] == '1';
+        const bool one_warp_rows = false;
+        static const int rows_variant = [] {                     // 4: four lanes per target (default), 2: producer /
+            const char* env = getenv("ORBITAL_B200_ROWS");        // consumer warps, 1: one warp per 32 targets
+            return env ? atoi(env) : 4;
         }();
-        if (!one_warp_rows && nb <= 148) {
+        if (!one_warp_rows && rows_variant == 4) {
+            static DeviceOnce rows4_attr;
+            if (rows4_attr.first()) {
+                cudaFuncSetAttribute(faithful_rows4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR4Smem);
+                cudaFuncSetAttribute(faithful_rows4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR4Smem);
+            }
+            if (fuse_tail)
+                faithful_rows4_kernel<true><<<nb, 128, kR4Smem, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl,
+                                                                      tail);
+            else
+                faithful_rows4_kernel<false><<<nb, 128, kR4Smem, st>>>(s.pos4, s.invr3, s.acc, s.n, s.invr3_ld, p.G, s.ctl,
+                                                                       tail);
+            return;
+        }
+        if (!one_warp_rows && rows_variant == 2 && nb <= 148) {
             static DeviceOnce rows2_attr;
             if (rows2_attr.first()) {
                 cudaFuncSetAttribute(faithful_rows2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2Smem);
