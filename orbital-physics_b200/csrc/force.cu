@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(32 * (1 + kR2Prod)) faithful_rows2_kernel(cons
     }
 }
 
-// Pass 2, four lanes per target (default).  The ordered sum is a chain of N dependent additions per target and
+// Pass 2, four lanes per target (ORBITAL_B200_ROWS=4; kept as a measured alternative and cross-check).  The ordered sum is a chain of N dependent additions per target and
 // component (8 cycles each: 17 us at N = 4,096); one warp doing everything for 32 targets has to issue 11 FP64 + 3 LDS
 // per source and is issue-bound at ~36 cycles per source, and handing finished terms from producer warps to a consumer
 // warp through shared memory (faithful_rows2_kernel) costs more in ring traffic and handshakes than it saves.  Here a
@@ -704,6 +704,8 @@ __global__ void __launch_bounds__(32 * (1 + kR2Prod)) faithful_rows2_kernel(cons
 // instruction each) and every lane then adds the 4 terms in source order, fetching them with shuffles -- the
 // accumulator is replicated in the 4 lanes, bit for bit.  Per source: 2 + 3 FP64 and 3 SHFL warp instructions, no
 // shared-memory stores, no cross-warp synchronisation beyond the TMA ring of matrix slabs the 4 warps of a CTA share.
+// Measured: 186 us per step at N = 4,096 against 108 -- the 12 shuffles per 4 sources cost more than the ring they
+// replace (SHFL issues at a fraction of the FP64 rate on this part), so this is not the default.
 constexpr int kR4Stages = 4;
 constexpr int kR4Smem = kR4Stages * (8192 + 1024) + 128;
 
@@ -859,12 +861,15 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
             cudaFuncSetAttribute(faithful_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
         }
         const RowsTail tail = {s.vel, s.vf32, s.hist, s.hist_cap, p.h};
-        const bool one_warp_rows = false;
-        static const int rows_variant = [] {                     // 4: four lanes per target (default), 2: producer /
-            const char* env = getenv("ORBITAL_B200_ROWS");        // consumer warps, 1: one warp per 32 targets
-            return env ? atoi(env) : 4;
-        }();
-        if (!one_warp_rows && rows_variant == 4) {
+        // pass-2 kernel: 2 = producer / consumer warps (default up to 148 column blocks), 1 = one warp per 32 targets
+        // (default above), 4 = four lanes per target.  Measured whole steps, us (profiles/r2_sweep_faithful_rows*.txt):
+        //   N      rows2   rows1   rows4          N       rows2*  rows1   rows4      (* falls back to rows1 above 148 blocks)
+        //   1,024   27.1    29.9    46.1          8,192    297.9   297.6   524.8
+        //   4,096  107.5   119.0   186.5         16,384    900.6   899.7  1984.7
+        const char* rows_env = getenv("ORBITAL_B200_ROWS");
+        const int rows_variant = rows_env ? atoi(rows_env) : 2;
+        const bool one_warp_rows = rows_variant == 1;
+        if (rows_variant == 4) {
             static DeviceOnce rows4_attr;
             if (rows4_attr.first()) {
                 cudaFuncSetAttribute(faithful_rows4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR4Smem);

@@ -312,6 +312,21 @@ def test_step_faithful_kernel_sequence_bit_exact(nat, orc, n):
     dev.close()
 
 
+@pytest.mark.parametrize("rows", ["1", "2", "4"])
+def test_faithful_pass2_variants_are_bit_identical(nat, orc, monkeypatch, rows):
+    """ORBITAL_B200_ROWS selects the pass-2 kernel of the two-pass bit-exact force (one warp per 32 targets,
+    producer / consumer warps, four lanes per target): all three equal the oracle bit for bit, ragged sizes too."""
+    from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_ROWS", rows)
+    for n in (513, 1000, 2048):
+        c = synthetic.random_cloud(n, seed=7 * n)
+        ref, _ = orc.pairwise(c["x"], c["y"], c["z"], c["m"], c["eps"], G, 1)
+        dev, a = device_accel(nat, c, nat.MODE_FAITHFUL)
+        assert_bits(a, ref, f"rows={rows} n={n}")
+        assert dev.step(3) == (3, 0)
+        dev.close()
+
+
 def test_disk4096_matches_reference_engine(nat, golden):
     """BASELINE config C1: the real reference's ctor + 2 steps at N=4096 (fixture) vs the faithful GPU path."""
     from core import synthetic
