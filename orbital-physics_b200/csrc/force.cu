@@ -397,14 +397,53 @@ __global__ void __launch_bounds__(256) faithful_pairs_kernel(const double4* __re
                                                              long long n, long long n_rows, double eps2, Ctl* ctl,
                                                              long long* pairs) {
     if (ctl->halted) return;
-    const int bi = blockIdx.y, bj = blockIdx.x;
-    if (bi > bj) return;
+    // triangular grid: block t -> tile (bi <= bj), t = bj (bj + 1) / 2 + bi
+    int bj = (int)((sqrtf(8.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
+    while ((long long)(bj + 1) * (bj + 2) / 2 <= (long long)blockIdx.x) ++bj;
+    while ((long long)bj * (bj + 1) / 2 > (long long)blockIdx.x) --bj;
+    const int bi = (int)((long long)blockIdx.x - (long long)bj * (bj + 1) / 2);
     __shared__ double tile[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const long long i0 = (long long)bi * 32, j0 = (long long)bj * 32;
     const long long j = j0 + tx;
     const double4 pj = pos4[min(j, n - 1)];
     const double Rj = DETECT ? radius[min(j, n - 1)] : 0.0;
+    if (bi < bj && j0 + 32 <= n) {
+        // Whole off-diagonal tile (all but ~2 n / 32 of the n^2 / 2048 tiles): every pair is valid, so no per-element
+        // predicates, and both copies of the tile are contiguous 8 KiB slabs addressed with 32-bit offsets.  The kernel
+        // is issue-bound (ncu: issue slots 71 % busy, FP64 pipe 36 %): 112 warp instructions per 32 pairs, only 31 of
+        // them FP64 / MUFU -- index arithmetic and predication are what there is to save.
+        __shared__ double4 srow[32];
+        __shared__ double srad[32];
+        if (ty == 0) {
+            srow[tx] = pos4[i0 + tx];
+            if (DETECT) srad[tx] = radius[i0 + tx];
+        }
+        __syncthreads();
+        double* dst = invr3 + ((long long)bj * n_rows + i0) * 32 + tx;        // rows i0.., column block bj
+        double* dstT = invr3 + ((long long)bi * n_rows + j0) * 32 + tx;       // rows j0.., column block bi (mirror)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = ty + 8 * k;
+            const double4 pi = srow[r];                                        // broadcast
+            const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y), dz = __dsub_rn(pj.z, pi.z);   // :145
+            const double r2 = __dadd_rn(dot3_numpy(dx, dy, dz), eps2);                                         // :146
+            const double inv_r = __ddiv_rn(1.0, __dsqrt_rn(r2));                                               // :147
+            const double v = __ddiv_rn(inv_r, r2);                                                             // :148
+            if (DETECT) {
+                if (overlap_exact(-dx, -dy, -dz, srad[r], Rj)) record_overlap(ctl, pairs, i0 + r, j);
+            }
+            dst[r * 32] = v;
+            tile[r][tx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = ty + 8 * k;
+            dstT[r * 32] = tile[tx][r];
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int r = ty + 8 * k;
@@ -849,11 +888,12 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
     if (s.invr3) {
         // two passes: pair matrix (each pair's sqrt/div once, overlap test included), then ordered row sums
         const int nb = (int)((s.n + 31) / 32);
+        const unsigned tri = (unsigned)((long long)nb * (nb + 1) / 2);     // tiles on or above the diagonal
         if (detect)
-            faithful_pairs_kernel<true><<<dim3(nb, nb), dim3(32, 8), 0, st>>>(s.pos4, s.radius, s.invr3, s.n, s.invr3_ld,
+            faithful_pairs_kernel<true><<<tri, dim3(32, 8), 0, st>>>(s.pos4, s.radius, s.invr3, s.n, s.invr3_ld,
                                                                               p.eps2, s.ctl, s.pairs);
         else
-            faithful_pairs_kernel<false><<<dim3(nb, nb), dim3(32, 8), 0, st>>>(s.pos4, s.radius, s.invr3, s.n,
+            faithful_pairs_kernel<false><<<tri, dim3(32, 8), 0, st>>>(s.pos4, s.radius, s.invr3, s.n,
                                                                                s.invr3_ld, p.eps2, s.ctl, s.pairs);
         static DeviceOnce rows_attr;
         if (rows_attr.first()) {

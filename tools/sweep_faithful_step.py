@@ -27,8 +27,8 @@ def step_us(c, steps):
     return 1e6 * best / steps, st
 
 
-which = {"1": "one warp per 32 targets", "2": "producer / consumer warps (up to 148 blocks)",
-         "4": "four lanes per target"}[os.environ.get("ORBITAL_B200_ROWS", "4")]
+which = {"1": "one warp per 32 targets", "2": "default: producer / consumer warps up to 148 blocks, one warp per 32 targets above",
+         "4": "four lanes per target"}[os.environ.get("ORBITAL_B200_ROWS", "2")]
 print(f"# pass 2 of the bit-exact force: {which} (ORBITAL_B200_ROWS = 4 | 2 | 1 selects; read once per process)")
 print(f"{'N':>6s} {'us/step':>10s} {'interactions/s':>15s}")
 for n in (65, 128, 256, 512, 1024, 2048, 4096, 8192, 16384):
