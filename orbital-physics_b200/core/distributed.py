@@ -147,7 +147,12 @@ class ShardedSystem:
     handle with device-side contact resolution -- sharded engines always resolve contacts on the device.
     """
 
-    def __init__(self, n: int, mode: int = _native.MODE_FAST, comm=None):
+    def __init__(self, n: int, mode: int = _native.MODE_FAST, comm=None, eager_state: bool = False):
+        """eager_state: complete the velocities and accelerations on every rank at the end of each `step()` / `accel()`
+        call, so that every later READ (download_state, download_acc, energy_angmom) is rank-local.  What
+        SimulationEngine uses under a DistComm: its reader threads (the app's contract) and ranks that inspect state
+        at different times must never start a collective on their own.  Costs two 24 B x N all-gathers per call."""
+        self.eager_state = bool(eager_state)
         self.comm = comm if comm is not None else DistComm()
         self.torch = self.comm.torch
         self.n, self.mode = int(n), int(mode)
@@ -168,6 +173,7 @@ class ShardedSystem:
         self._partial = bool(self.dev.acc_needs_allreduce()) and self.world > 1
         self._detect = False
         self._acc_full = True
+        self._vel_full = True
         self.steps_done = 0
         self.events = None             # set to {} to collect (start, end) CUDA events per phase: "gather", "reduce",
                                        # "force" (bench.py); rank-local handles only
@@ -227,6 +233,11 @@ class ShardedSystem:
         for d in self.devs:
             d.upload(x, y, z, vx, vy, vz, m, radius, vel_is_f32)
         self._detect = bool(np.any(np.asarray(radius) > 0.0))
+        self._m = np.array(m, dtype=np.float64, copy=True)
+        self._vel_full = True
+
+    def _masses(self):
+        return self._m
 
     def _gather_rows3(self, views):
         """Make rows [3, n] complete on every rank from the per-rank slabs (velocities, accelerations)."""
@@ -248,9 +259,19 @@ class ShardedSystem:
             self.comm.all_gather_rows([tmp], self.per)
             v[c].copy_(tmp[: self.n])
 
-    def download_state(self, out=None):
-        """Full x y z vx vy vz (positions are complete on every rank; velocities are gathered first)."""
+    def _complete_state(self):
+        """Velocities and accelerations complete on every rank (collective)."""
         self._gather_rows3(self._vel)
+        if not self._acc_full:
+            self._gather_rows3(self._acc)
+            self._acc_full = True
+        self._vel_full = True
+
+    def download_state(self, out=None):
+        """Full x y z vx vy vz (positions are complete on every rank; velocities are gathered first unless the
+        last step already did)."""
+        if not (self.eager_state and self._vel_full):
+            self._gather_rows3(self._vel)
         return self.dev.download_state(out)
 
     def download_acc(self):
@@ -302,6 +323,8 @@ class ShardedSystem:
         for d in self.devs:
             d.accel()
         self._reduce_acc()
+        if self.eager_state:
+            self._complete_state()
 
     def _contacts(self) -> int:
         """engine.py:85 across ranks. Returns the number of candidate pairs handed to the sweep (0: none)."""
@@ -334,6 +357,9 @@ class ShardedSystem:
             for d in self.devs:
                 d.step_end()
         self.steps_done += int(nsteps)
+        self._vel_full = False
+        if self.eager_state and nsteps:
+            self._complete_state()
         resolved = self.dev.contact_stats()["contacts_total"] - before if self._detect else 0
         return int(nsteps), int(resolved)
 
@@ -353,7 +379,15 @@ class ShardedSystem:
         return self.dev.potential()
 
     def energy_angmom(self):
-        """(K, L[3]) summed over ranks in rank order (engine.py:104-121)."""
+        """(K, L[3]) (engine.py:104-121): per-rank device reductions summed in rank order -- or, with eager_state,
+        evaluated from the complete local state without any collective."""
+        if self.eager_state and self._vel_full:
+            st = self.dev.download_state()
+            m = self._masses()
+            K = float(0.5 * np.sum(m * (st["vx"] ** 2 + st["vy"] ** 2 + st["vz"] ** 2)))
+            r = np.stack([st["x"], st["y"], st["z"]], 1)
+            p = np.stack([st["vx"], st["vy"], st["vz"]], 1) * m[:, None]
+            return K, np.cross(r, p).sum(axis=0)
         parts = [d.energy_angmom() for d in self.devs]
         local = [np.concatenate([[k], L]) for k, L in parts]
         every = self.comm.all_gather_host(local)

@@ -236,7 +236,8 @@ class SimulationEngine:
             self._comm = distributed.make_comm(self._devices)
         if self._comm.world == 1:
             return _native.DeviceSystem(n, next(iter(self._comm.devices.values())), mode)
-        return distributed.ShardedSystem(n, mode, self._comm)
+        # one process per GPU: reads must never start a collective (reader threads, ranks out of step) -> eager state
+        return distributed.ShardedSystem(n, mode, self._comm, eager_state=isinstance(self._comm, distributed.DistComm))
 
     # ------------------------------------------------------------ lazy mirroring
     # After a step the device is ahead of the Python objects.  The first attribute read of ANY bound object pulls

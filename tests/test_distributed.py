@@ -239,3 +239,38 @@ def test_fast_sharded_over_two_real_gpus_in_one_process(orc):
     rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
     assert rel.max() <= 1e-12
     sh.close()
+
+
+def _engine_dist_worker(rank, world, port, name):
+    for p in (os.path.join(REPO, "orbital-physics_b200"), REPO):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from core import _native, distributed
+    from tests.fake_device import FakeDeviceSystem
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _native.DeviceSystem = FakeDeviceSystem
+    distributed.ShardedSystem = _fake_sharded_class(torch, partial=False)
+    from tests.test_engine import build_engine, check_against_golden
+    g = np.load(os.path.join(REPO, "tests", "golden", name + ".npz"))
+    eng = build_engine(g, devices="dist")
+    assert eng._dev.world == world and eng._dev.eager_state
+    check_against_golden(g, eng)                     # every rank holds, and checks, the complete state
+    eng.run(3)
+    if rank == 0:
+        # reads are rank-local in this mode: one rank (or a reader thread) may look at the state on its own
+        _ = eng.objects[1].position(), eng.objects[2].velocity, eng.total_energy(), eng.history[eng.objects[0].uuid]
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["coll_dense_mixed", "mixed12"])
+def test_engine_one_process_per_rank_gloo(name):
+    """SimulationEngine(devices="dist") under torch.distributed (gloo, 2 ranks, oracle stand-in): the reference's own
+    outputs bit for bit on every rank, and state reads that involve no collective."""
+    import torch.multiprocessing as mp
+    mp.spawn(_engine_dist_worker, args=(2, _free_port(), name), nprocs=2, join=True)
