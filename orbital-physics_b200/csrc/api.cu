@@ -89,7 +89,11 @@ struct orb_engine {
 
 namespace {
 
-constexpr int kGraphSteps = 16;
+static const int kGraphSteps = [] {            // steps per replayed graph (ORBITAL_B200_GRAPH_STEPS)
+    const char* env = getenv("ORBITAL_B200_GRAPH_STEPS");
+    const int v = env ? atoi(env) : 16;
+    return v >= 2 && v <= 1024 ? v : 16;
+}();
 
 void drop_graphs(orb_engine* e) {
     if (e->graph1) { cudaGraphExecDestroy(e->graph1); e->graph1 = nullptr; }
@@ -922,7 +926,11 @@ struct orb_ensemble {
 };
 
 namespace {
-constexpr int kEnsGraphSteps = 16;
+static const int kEnsGraphSteps = [] {         // un-fused ensemble steps per replayed graph (ORBITAL_B200_ENS_GRAPH_STEPS)
+    const char* env = getenv("ORBITAL_B200_ENS_GRAPH_STEPS");
+    const int v = env ? atoi(env) : 16;
+    return v >= 2 && v <= 1024 ? v : 16;
+}();
 constexpr int kEnsBranches = 4;          // independent sub-batches of a small ensemble inside one step graph
 
 void ens_drop_graph(orb_ensemble* s) {
