@@ -294,8 +294,14 @@ __device__ __forceinline__ void sym_reduce_row(const double* __restrict__ Pi, co
     const long long X = x / B;
     const long long T = x / tile;
     double s[3] = {0.0, 0.0, 0.0};
-    if (X % world == rank) {
-        const long long kx = (X - rank) / world;
+    // ownership (multi-GPU): every group of `world` consecutive I-blocks gives one block to each rank, in ascending
+    // rank order in even groups and descending order in odd ones ("snake"), which balances the triangle: block I
+    // costs ~(N - I B) B pairs, so plain cyclic ownership hands rank 0 a whole group-width more work per group than
+    // the last rank (5.5 % of the pass at N = 262,144 on 8 ranks).
+    const long long gx = X / world;
+    const int posx = (int)(X - gx * world);
+    if (((gx & 1) ? world - 1 - posx : posx) == rank) {
+        const long long kx = gx;
         if (kx >= ka && kx < kb) {
             const int c_first = (int)(((X * B) / tile) / chunk_tiles);
             for (int c = c_first + sub; c < n_chunks; c += kRedSplit) {
@@ -304,9 +310,12 @@ __device__ __forceinline__ void sym_reduce_row(const double* __restrict__ Pi, co
             }
         }
     }
-    // owned I-blocks that treated x's tile symmetrically: I < nI  <=>  k < ceil((nI - rank) / world)
+    // owned I-blocks that treated x's tile symmetrically: I_k < nI, I_k = world k + pos(k): all full groups below nI,
+    // plus the partial group if this rank's block in it comes before nI
     const long long nI = (T * tile) / B;
-    long long kend = nI > rank ? (nI - rank + world - 1) / world : 0;
+    const long long gI = nI / world;
+    const int rem = (int)(nI - gI * world);
+    long long kend = gI + ((((gI & 1) ? world - 1 - rank : rank) < rem) ? 1 : 0);
     if (kend > kb) kend = kb;
     for (long long k = ka + sub; k < kend; k += kRedSplit) {
 #pragma unroll
@@ -335,7 +344,7 @@ struct SymTail {
 };
 
 // a[x] (+)= G * ( sum_{chunks of x's I-block} P_i[chunk][x] + sum_{owned I-blocks of this panel before x} P_j[slot][x] )
-// I-blocks are owned cyclically: I = rank + world * k; the panel holds k in [ka, kb).
+// I-blocks are owned group-wise in snake order: I_k = world k + (k odd ? world-1-rank : rank); the panel holds k in [ka, kb).
 __global__ void __launch_bounds__(256) reduce_sym_kernel(const double* __restrict__ Pi, const double* __restrict__ Pj,
                                                          double* acc, long long n, long long B, int tile,
                                                          int chunk_tiles, int n_chunks, int rank, int world, int ka,
@@ -510,7 +519,10 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
     if (occ <= 0) occ = 2;
     p.ctas_per_sm = occ;
     const long long slots = (long long)sm_count * occ;
-    const int my_blocks = (p.nb_I - rank + world - 1) / world;      // I-blocks owned by this rank (cyclic)
+    // I-blocks owned by this rank: one per group of `world` blocks, snake order (see reduce_sym_kernel)
+    auto owned_block = [&](int k) { return world * k + ((k & 1) ? world - 1 - rank : rank); };
+    int my_blocks = 0;
+    while (owned_block(my_blocks) < p.nb_I) ++my_blocks;                     // owned_block is increasing in k
     // panels: bound the P_j footprint (one 3 x n plane per owned I-block of the panel)
     long long budget = 16LL << 30;
     const char* env_b = getenv("ORBITAL_B200_SYM_PJ_BYTES");
@@ -534,7 +546,7 @@ cudaError_t plan_sym(SymPlan& p, long long n, int sm_count, int rank, int world)
         pan.kb = std::min(my_blocks, ka + p.panel_blocks);
         std::vector<SymItem> items;
         for (int k = pan.ka; k < pan.kb; ++k) {
-            const int I = rank + world * k;
+            const int I = owned_block(k);
             const int first_tile = (int)(((long long)I * p.B) / p.tile);
             for (int c = first_tile / p.chunk_tiles; c < p.n_chunks; ++c) {
                 SymItem it;
