@@ -7,7 +7,7 @@ metric  : pairwise interactions/s (fp64), N^2 ordered interactions per force eva
           one force evaluation per leapfrog step.
 workload: N=1 GPU  -> BASELINE configs[2]: Plummer sphere N=262,144, fast (roofline) kernel.
           N>1 GPUs -> BASELINE configs[4]: Plummer sphere N=2,097,152 over the ranks (strong scaling): every
-                      unordered pair is evaluated once, pair blocks owned cyclically by rank; per step an
+                      unordered pair is evaluated once, pair blocks dealt to the ranks in snake order; per step an
                       all-gather of the packed positions (32 B x N) and a reduce-scatter of the partial
                       accelerations (24 B x N in, every rank keeps its slab) over NCCL.
 A "step" is one pass of the hot path: half-kick+drift -> force -> half-kick, through the C ABI.
@@ -68,7 +68,7 @@ def parse_args():
 def workload(args):
     n = args.n_bodies or (262144 if args.gpus == 1 else 2097152)
     name = (f"Plummer sphere N={n} all-pairs force + leapfrog step"
-            + ("" if args.gpus == 1 else f", every unordered pair once, pair blocks owned cyclically by {args.gpus} ranks, "
+            + ("" if args.gpus == 1 else f", every unordered pair once, pair blocks dealt in snake order to {args.gpus} ranks, "
                                          "all-gather 32 B x N + reduce-scatter (all-reduce below 1M bodies) 24 B x N per step (NCCL)"))
     return n, name
 
@@ -674,7 +674,7 @@ def run_ours(args):
         "config": {"workload": name, "n_bodies": n, "mode": "fast", "ic": "Plummer (Aarseth-Henon-Wielen), seed=N",
                    "interactions_per_step": "N^2", "l2": "flushed between steps (256 MiB memset)",
                    "parallelism": "1 GPU" if world == 1 else
-                                  f"cyclic pair-block ownership x{world}, all-gather 32 B x N + reduce-scatter / all-reduce 24 B x N"},
+                                  f"snake-order pair-block ownership x{world}, all-gather 32 B x N + reduce-scatter / all-reduce 24 B x N"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity_check": parity,
     }

@@ -167,7 +167,7 @@ int orb_set_overlap_pairs(orb_engine* e, const int64_t* pairs_ij, int64_t count,
  * pairs. */
 int orb_contact_stats(orb_engine* e, int64_t* contacts_total, int64_t* full_sweeps);
 /* *flag != 0: on this (sharded, fast-mode) engine orb_accel leaves a PARTIAL acceleration of all n bodies
- * (the pair-symmetric kernel evaluates a cyclic share of the pair blocks per rank); the caller must
+ * (the pair-symmetric kernel evaluates every world-th pair block per rank); the caller must
  * all-reduce (sum) the 3 x n buffer at orb_acc_ptr across ranks before orb_step_kick. orb_step_finish is
  * not available then. */
 int orb_acc_needs_allreduce(orb_engine* e, int* flag);

@@ -15,7 +15,7 @@ slab of ceil(N / world) bodies.  One leapfrog step (reference core/engine.py:65-
 
 Bit-exact mode: every rank evaluates its own targets against all sources; a target's source order does
 not depend on the partition, so the result is bit-identical to one GPU.  Fast mode: the pair-symmetric
-kernel evaluates every unordered pair once, so each rank takes a cyclic share of the pair blocks and
+kernel evaluates every unordered pair once, so each rank takes every world-th pair block (snake order, which balances the triangle) and
 produces a partial acceleration of all N bodies; a reduce-scatter gives every rank the total for its slab.
 
 Two communicators carry the same protocol:

@@ -108,7 +108,7 @@ bool sym_applicable(const orb_engine* e) {
     return e->mode == ORB_MODE_FAST && e->use_sym && (!e->sharded || e->world > 0);
 }
 
-// pair-symmetric force on a sharded engine: every rank evaluates a cyclic share of the I-blocks and
+// pair-symmetric force on a sharded engine: every rank evaluates its share of the I-blocks (one per group of `world`, snake order) and
 // ends up with a PARTIAL acceleration of all n bodies; the caller all-reduces (sum) acc across ranks.
 bool acc_is_partial(const orb_engine* e) { return e->sharded && sym_applicable(e); }
 

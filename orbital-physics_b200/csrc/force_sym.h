@@ -25,7 +25,7 @@ struct SymPlan {
     bool valid = false;
     int ti = 4;
     long long n = 0;
-    int rank = 0, world = 1;  // cyclic ownership of I-blocks (multi-GPU); 0/1 on one GPU
+    int rank = 0, world = 1;  // snake-order ownership of I-blocks (multi-GPU); 0/1 on one GPU
     long long B = 0;          // bodies per I-block (128 * ti)
     int nb_I = 0, n_tiles = 0;
     int tile = 256;           // bodies per source tile (64 / 128 / 256)

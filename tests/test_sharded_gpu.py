@@ -1,7 +1,7 @@
 """The multi-GPU (sharded) CUDA path, held to the oracle on ONE device  (`-m gpu`).
 
 `LocalComm([0] * world)` creates `world` handles with orb_create_ranked on device 0 and runs the real per-rank
-launch sequence of a `world`-GPU job -- orb_step_begin / orb_step_force (cyclic pair-block ownership in
+launch sequence of a `world`-GPU job -- orb_step_begin / orb_step_force (snake-order pair-block ownership in
 force_sym_kernel + reduce_sym_kernel, or the target-slab kernels) / orb_step_kick / orb_step_end -- with the
 all-gather and all-reduce replaced by device-to-device copies and a fixed-order sum (core/distributed.py).
 Only the transport differs from an NCCL run, so these tests are the parity evidence for BASELINE configs[4]
@@ -89,7 +89,7 @@ def test_sharded_faithful_bit_exact_vs_oracle(nat, orc, world, n):
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("n,masses", [(4096, "general"), (6000, "general"), (12288, "uniform"), (4099, "general")])
 def test_sharded_fast_all_rows_within_tolerance(nat, orc, world, n, masses):
-    """Pair-symmetric kernel with cyclic I-block ownership per rank (plan_sym rank/world, reduce_sym_kernel) and
+    """Pair-symmetric kernel with snake-order I-block ownership per rank (plan_sym rank/world, reduce_sym_kernel) and
     the all-reduce of the partial accelerations: every row <= 1e-12 of the oracle at the SAME positions, each of
     3 steps; n=6000 / 4099 have ragged tiles, I-blocks and slabs, n=12288 takes the uniform-mass variant."""
     c, m, f32, vel = cloud(n, masses)
