@@ -224,8 +224,8 @@ int orb_ens_upload(orb_ensemble* s, const double* x, const double* y, const doub
  * mass at rest at the origin; bodies 1.. are parent-relative with
  * n = sqrt(G m_0 / a^3) (core/body.py:159-169) and b = a sqrt(1-e^2) (:120-124).
  * Element arrays are [nsys][nbody-1] (radians, metres); m is [nsys][nbody].
- * Same operation order as the reference; differs from it only where the device
- * sin/cos differ from the host libm (<= 2 ulp) -- within tolerance, not bit-exact. */
+ * Same operation order as the reference; sin/cos as orb_set_trig_mode selects
+ * (default ORB_TRIG_LIBM: bit-identical to the reference on an x86-64 glibc host). */
 int orb_ens_upload_elements(orb_ensemble* s, const double* M, const double* e, const double* a,
                             const double* inc, const double* Omega, const double* omega,
                             const double* m);
@@ -249,7 +249,25 @@ int orb_ens_launch_count(orb_ensemble* s, int64_t* launches);
  * host arrays in (M, inc, Omega, omega in radians; a, b in metres; n = mean
  * motion in rad/s), host arrays out (r3, v3: [3][count]; E optional: eccentric
  * anomaly). Replaces a Python loop over Body.get_state (core/body.py:184-249)
- * / solve_kepler(M, e, tol, max_iter) (core/physics.py:43-71). */
+ * / solve_kepler(M, e, tol, max_iter) (core/physics.py:43-71).
+ *
+ * The reference's math.sin / math.cos (core/body.py:218-223, core/physics.py:63)
+ * are the host libm's; orb_set_trig_mode picks what stands in for them on the
+ * device, process-wide (start value: env ORBITAL_B200_TRIG = libm | cr | fast):
+ *   ORB_TRIG_LIBM  glibc 2.39 sin/cos restated operation by operation
+ *                  (csrc/sincos_libm.h): states bit-identical to the reference
+ *                  on an x86-64 glibc host with FMA. Default.
+ *   ORB_TRIG_CR    correctly rounded sin/cos (csrc/sincos_cr.h): host independent.
+ *   ORB_TRIG_FAST  CUDA sincos (<= 2 ulp): tolerance path.
+ * The two integer powers of the reference's IC code, e ** 2 (core/body.py:216)
+ * and a ** 3 (core/body.py:166), are CPython float pow = the host libm's pow(),
+ * which is not correctly rounded either; the library evaluates them with the
+ * same host pow() (one call per body, before the launch). */
+#define ORB_TRIG_LIBM 0
+#define ORB_TRIG_CR 1
+#define ORB_TRIG_FAST 2
+int orb_set_trig_mode(int mode);
+int orb_get_trig_mode(void);
 int orb_kepler_states(int device, int64_t count, const double* M, const double* e, const double* a,
                       const double* b, const double* n, const double* inc, const double* Omega,
                       const double* omega, double tol, int max_iter,

@@ -66,32 +66,36 @@ def rows_vectorised(pos: np.ndarray, m: np.ndarray, rows, eps: float, G: float =
     return out
 
 
-def solve_kepler(M: float, e: float, tol: float = 1e-12, max_iter: int = 50) -> float:
-    """physics.py:43-71: Newton on E - e sin E = M, start at M (e < 0.8) or pi; test |dE| after the update."""
+def solve_kepler(M: float, e: float, tol: float = 1e-12, max_iter: int = 50, sin=math.sin, cos=math.cos) -> float:
+    """physics.py:43-71: Newton on E - e sin E = M, start at M (e < 0.8) or pi; test |dE| after the update.
+    `sin` / `cos`: the reference calls the host libm (the default); tests pass the correctly rounded pair
+    (csrc/sincos_cr.h built for the host) to get the exact bits the device pipeline must produce."""
     E = M if e < 0.8 else math.pi
     for _ in range(max_iter):
-        dE = -(E - e * math.sin(E) - M) / (1.0 - e * math.cos(E))
+        dE = -(E - e * sin(E) - M) / (1.0 - e * cos(E))
         E += dE
         if abs(dE) < tol:
             break
     return E
 
 
-def kepler_states(M, e, a, b, n, inc, Omega, omega, tol: float = 1e-12, max_iter: int = 50):
-    """body.py:184-249 over arrays: parent-relative (r[count,3], v[count,3], E[count]) with host libm trig."""
+def kepler_states(M, e, a, b, n, inc, Omega, omega, tol: float = 1e-12, max_iter: int = 50, sin=math.sin,
+                  cos=math.cos):
+    """body.py:184-249 over arrays: parent-relative (r[count,3], v[count,3], E[count]); trig = host libm unless
+    `sin` / `cos` are given (see solve_kepler)."""
     cnt = len(M)
     r, v, Eo = np.empty((cnt, 3)), np.empty((cnt, 3)), np.empty(cnt)
     for k in range(cnt):
         ek, ak, bk, nk = float(e[k]), float(a[k]), float(b[k]), float(n[k])
-        E = solve_kepler(float(M[k]), ek, tol, max_iter)
-        cE, sE = math.cos(E), math.sin(E)
+        E = solve_kepler(float(M[k]), ek, tol, max_iter, sin, cos)
+        cE, sE = cos(E), sin(E)
         x_op = ak * (cE - ek)
         y_op = bk * sE
         vx_op = -ak * nk * sE / (1 - ek * cE)
         vy_op = ak * nk * math.sqrt(1 - ek ** 2) * cE / (1 - ek * cE)
-        cw, sw = math.cos(float(omega[k])), math.sin(float(omega[k]))
-        ci, si = math.cos(float(inc[k])), math.sin(float(inc[k]))
-        cO, sO = math.cos(float(Omega[k])), math.sin(float(Omega[k]))
+        cw, sw = cos(float(omega[k])), sin(float(omega[k]))
+        ci, si = cos(float(inc[k])), sin(float(inc[k]))
+        cO, sO = cos(float(Omega[k])), sin(float(Omega[k]))
         R = ((cO * cw - sO * sw * ci, -cO * sw - sO * cw * ci, sO * si),
              (sO * cw + cO * sw * ci, -sO * sw + cO * cw * ci, -cO * si),
              (sw * si, cw * si, ci))
@@ -102,7 +106,7 @@ def kepler_states(M, e, a, b, n, inc, Omega, omega, tol: float = 1e-12, max_iter
     return r, v, Eo
 
 
-def ensemble_from_elements(M, e, a, inc, Omega, omega, m, G: float = G_SI):
+def ensemble_from_elements(M, e, a, inc, Omega, omega, m, G: float = G_SI, sin=math.sin, cos=math.cos):
     """What orb_ens_upload_elements builds: central body at rest at the origin, the others parent-relative with
     n = sqrt(G m_0 / a**3) (body.py:159-169) and b = a sqrt(1 - e**2) (body.py:120-124). Arrays [nsys, nbody-1]."""
     nsys, k = np.shape(M)
@@ -111,7 +115,7 @@ def ensemble_from_elements(M, e, a, inc, Omega, omega, m, G: float = G_SI):
         mu = G * float(m[s, 0])
         nn = np.array([math.sqrt(mu / float(a[s, j]) ** 3) for j in range(k)])
         bb = np.array([float(a[s, j]) * math.sqrt(1 - float(e[s, j]) ** 2) for j in range(k)])
-        r, v, _ = kepler_states(M[s], e[s], a[s], bb, nn, inc[s], Omega[s], omega[s])
+        r, v, _ = kepler_states(M[s], e[s], a[s], bb, nn, inc[s], Omega[s], omega[s], sin=sin, cos=cos)
         for c, key in enumerate(("x", "y", "z")):
             out[key][s, 1:] = r[:, c]
         for c, key in enumerate(("vx", "vy", "vz")):

@@ -97,6 +97,8 @@ SIGNATURES = {
     "orb_ens_energy": (C.c_int, [_vp, _f64]),
     "orb_ens_synchronize": (C.c_int, [_vp]),
     "orb_ens_launch_count": (C.c_int, [_vp, _i64p]),
+    "orb_set_trig_mode": (C.c_int, [C.c_int]),
+    "orb_get_trig_mode": (C.c_int, []),
     "orb_kepler_states": (C.c_int, [C.c_int, C.c_int64] + [_f64] * 8 + [C.c_double, C.c_int, _f64, _f64, _vp]),
 }
 
@@ -394,6 +396,20 @@ class DeviceSystem:
         got = C.c_int64(0)
         check(lib().orb_history_download(self._h, last_k, _ptr(out.reshape(-1)) if last_k > 0 else None, C.byref(got)))
         return out[: got.value]
+
+
+TRIG_LIBM, TRIG_CR, TRIG_FAST = 0, 1, 2          # ORB_TRIG_* (include/orbital_b200.h)
+_TRIG_NAMES = {"libm": TRIG_LIBM, "cr": TRIG_CR, "fast": TRIG_FAST}
+
+
+def set_trig_mode(mode) -> None:
+    """What stands in for the reference's math.sin / math.cos in the device IC pipeline: "libm" (default, glibc
+    2.39 restated -> bit-identical states on an x86-64 glibc host), "cr" (correctly rounded), "fast" (CUDA sincos)."""
+    check(lib().orb_set_trig_mode(int(_TRIG_NAMES.get(mode, mode))))
+
+
+def get_trig_mode() -> int:
+    return int(lib().orb_get_trig_mode())
 
 
 def kepler_states(M, e, a, b, n, inc, Omega, omega, tol: float = 1e-12, max_iter: int = 50, device: int = 0,

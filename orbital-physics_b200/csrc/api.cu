@@ -3,18 +3,47 @@
 // single-CTA kernel), history ring, diagnostics.  No CPU compute path exists:
 // every entry point that computes needs a CUDA device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/orbital_b200.h"
 #include "ensemble.h"
 #include "force_sym.h"
 #include "kernels.h"
+
+// which sin / cos the initial-condition kernels use (kepler.cu); process-wide, ORBITAL_B200_TRIG sets the start value
+static std::atomic<int> g_trig{-1};
+static int trig_mode() {
+    int t = g_trig.load(std::memory_order_relaxed);
+    if (t < 0) {
+        const char* env = getenv("ORBITAL_B200_TRIG");
+        t = ORB_TRIG_LIBM;
+        if (env && !strcmp(env, "cr")) t = ORB_TRIG_CR;
+        if (env && !strcmp(env, "fast")) t = ORB_TRIG_FAST;
+        g_trig.store(t, std::memory_order_relaxed);
+    }
+    return t;
+}
+
+// x ** y as CPython evaluates it: the host libm's pow().  The reference's IC code has two integer powers,
+// e ** 2 (core/body.py:216) and a ** 3 (core/body.py:166); glibc's pow is < 1 ulp but not correctly rounded
+// (0.08 % of squares differ from e * e), and unlike sin / cos its table-driven algorithm is not restated for
+// the device, so these two scalars per body are formed here, on the host, and travel with the elements.
+static void host_pow_plane(const double* x, double y, double* out, int64_t n) {
+    const int nt = n >= (1 << 16) ? (int)std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    auto work = [=](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) out[i] = pow(x[i], y); };
+    if (nt == 1) return work(0, n);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto& t : th) t.join();
+}
 
 using namespace orb;
 
@@ -1190,15 +1219,18 @@ int orb_ens_upload_elements(orb_ensemble* s, const double* M, const double* e, c
     const size_t pb = sizeof(double) * pl;
     cudaStream_t st = s->stream;
     double* d_el = nullptr;
-    CU(cudaMalloc(&d_el, 6 * pb));
-    const double* src[6] = {M, e, a, inc, Omega, omega};
+    CU(cudaMalloc(&d_el, 8 * pb));
+    std::vector<double> e2(pl), a3(pl);
+    host_pow_plane(e, 2.0, e2.data(), pl);
+    host_pow_plane(a, 3.0, a3.data(), pl);
+    const double* src[8] = {M, e, a, inc, Omega, omega, e2.data(), a3.data()};
     cudaError_t ce = cudaSuccess;
-    for (int k = 0; k < 6 && ce == cudaSuccess; ++k)
+    for (int k = 0; k < 8 && ce == cudaSuccess; ++k)
         ce = cudaMemcpyAsync(d_el + k * pl, src[k], pb, cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess)
         ce = cudaMemcpyAsync(const_cast<double*>(s->a.m), m, sizeof(double) * s->a.nsys * s->a.nb,
                              cudaMemcpyHostToDevice, st);
-    if (ce == cudaSuccess) ce = launch_ens_elements(s->a, d_el, 1e-12, 50, st);       // physics.py:43 defaults
+    if (ce == cudaSuccess) ce = launch_ens_elements(s->a, d_el, 1e-12, 50, trig_mode(), st);       // physics.py:43 defaults
     EnsArgs a0 = s->a;
     a0.nsteps = 0;
     if (ce == cudaSuccess) ce = launch_ens_accel(a0, s->mode == ORB_MODE_FAITHFUL, st);   // engine.py:41
@@ -1209,6 +1241,15 @@ int orb_ens_upload_elements(orb_ensemble* s, const double* M, const double* e, c
     s->have_state = true;
     return ORB_OK;
 }
+
+int orb_set_trig_mode(int mode) {
+    if (mode != ORB_TRIG_LIBM && mode != ORB_TRIG_CR && mode != ORB_TRIG_FAST)
+        return fail(ORB_ERR_INVALID, "trig mode must be ORB_TRIG_LIBM, ORB_TRIG_CR or ORB_TRIG_FAST");
+    g_trig.store(mode, std::memory_order_relaxed);
+    return ORB_OK;
+}
+
+int orb_get_trig_mode(void) { return trig_mode(); }
 
 int orb_kepler_states(int device, int64_t count, const double* M, const double* e, const double* a, const double* b,
                       const double* n, const double* inc, const double* Omega, const double* omega, double tol,
@@ -1221,12 +1262,14 @@ int orb_kepler_states(int device, int64_t count, const double* M, const double* 
     if (rc) return rc;
     const size_t pb = sizeof(double) * count;
     double *d_el = nullptr, *d_out = nullptr;
-    CU(cudaMalloc(&d_el, 8 * pb));
+    CU(cudaMalloc(&d_el, 9 * pb));
     cudaError_t ce = cudaMalloc(&d_out, 7 * pb);
-    const double* src[8] = {M, e, a, b, n, inc, Omega, omega};
-    for (int k = 0; k < 8 && ce == cudaSuccess; ++k)
+    std::vector<double> e2(count);
+    host_pow_plane(e, 2.0, e2.data(), count);
+    const double* src[9] = {M, e, a, b, n, inc, Omega, omega, e2.data()};
+    for (int k = 0; k < 9 && ce == cudaSuccess; ++k)
         ce = cudaMemcpy(d_el + k * count, src[k], pb, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = launch_kepler_states(d_el, d_out, count, tol, max_iter, nullptr);
+    if (ce == cudaSuccess) ce = launch_kepler_states(d_el, d_out, count, tol, max_iter, trig_mode(), nullptr);
     if (ce == cudaSuccess) ce = cudaMemcpy(r3, d_out, 3 * pb, cudaMemcpyDeviceToHost);
     if (ce == cudaSuccess) ce = cudaMemcpy(v3, d_out + 3 * count, 3 * pb, cudaMemcpyDeviceToHost);
     if (ce == cudaSuccess && E) ce = cudaMemcpy(E, d_out + 6 * count, pb, cudaMemcpyDeviceToHost);

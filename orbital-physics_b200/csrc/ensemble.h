@@ -26,7 +26,9 @@ cudaError_t launch_ens_step_sliced(const EnsArgs& a, int slice, unsigned long lo
 cudaError_t launch_ens_accel(const EnsArgs& a, bool faithful, cudaStream_t st);
 cudaError_t launch_ens_energy(const EnsArgs& a, double* E, cudaStream_t st);
 // kepler.cu: Keplerian elements -> Cartesian state (core/physics.py:43-71, core/body.py:184-249)
-cudaError_t launch_kepler_states(const double* d_el8, double* d_out7, long long count, double tol, int max_iter,
-                                 cudaStream_t st);
-cudaError_t launch_ens_elements(const EnsArgs& a, const double* d_el6, double tol, int max_iter, cudaStream_t st);
+// trig: ORB_TRIG_* (include/orbital_b200.h) -- which sin / cos stands in for the reference's math.sin / math.cos
+cudaError_t launch_kepler_states(const double* d_el9, double* d_out7, long long count, double tol, int max_iter,
+                                 int trig, cudaStream_t st);
+cudaError_t launch_ens_elements(const EnsArgs& a, const double* d_el8, double tol, int max_iter, int trig,
+                                cudaStream_t st);
 }  // namespace orb

@@ -669,29 +669,74 @@ def test_graph_replay_on_the_legacy_default_stream(nat):
 def test_kepler_states_device_vs_reference(nat, golden):
     """Batched elements -> state on the device vs the reference's Body.get_state outputs (kepler_batch.npz).
 
-    Same operation order; only the device sin/cos can differ from the host libm, so the bar is a tolerance:
-    |dE| <= 4e-15/(1-e) and relative state error <= 1e-13 (measured ~1e-15); most entries are bit-identical."""
+    Same operation order as body.py:184-249; the trig mode decides the rest:
+      libm (default)  glibc's sin/cos restated (csrc/sincos_libm.h): EVERY state and eccentric anomaly bit-identical
+                      to what the unmodified reference produced on this image's host;
+      cr              correctly rounded sin/cos (csrc/sincos_cr.h): bit-identical to the oracle pipeline run with the
+                      host build of the same routine, > 99 % of the golden states;
+      fast            CUDA sincos: |dE| <= 4e-15/(1-e), relative state error <= 1e-13."""
+    from oracle import ref_numpy
+    from tests.test_sincos import build_host_trig, scalar_trig
     g = golden("kepler_batch")
-    r, v, E = nat.kepler_states(*(g[k] for k in ("M", "e", "a", "b", "n", "inc", "Omega", "omega")), return_E=True)
+    cols = [g[k] for k in ("M", "e", "a", "b", "n", "inc", "Omega", "omega")]
+    assert nat.get_trig_mode() == nat.TRIG_LIBM
+    r, v, E = nat.kepler_states(*cols, return_E=True)
+    assert_bits(E, g["E"], "eccentric anomaly, libm mode")
+    assert_bits(r, g["r"], "positions, libm mode")
+    assert_bits(v, g["v"], "velocities, libm mode")
+    try:
+        nat.set_trig_mode("cr")
+        r, v, E = nat.kepler_states(*cols, return_E=True)
+        sin, cos = scalar_trig(build_host_trig(), "sc_host_sincos")
+        rr, vv, EE = ref_numpy.kepler_states(*cols, sin=sin, cos=cos)
+        assert_bits(E, EE, "eccentric anomaly, cr mode"); assert_bits(r, rr, "r, cr mode"); assert_bits(v, vv, "v, cr mode")
+        exact_cr = np.mean(np.all(r == g["r"], axis=1) & np.all(v == g["v"], axis=1))
+        assert exact_cr > 0.98
+        nat.set_trig_mode("fast")
+        r, v, E = nat.kepler_states(*cols, return_E=True)
+    finally:
+        nat.set_trig_mode("libm")
     dE = np.abs(E - g["E"]) * (1.0 - g["e"])
     er = np.linalg.norm(r - g["r"], axis=1) / np.linalg.norm(g["r"], axis=1)
     ev = np.linalg.norm(v - g["v"], axis=1) / np.linalg.norm(g["v"], axis=1)
     exact = np.mean(np.all(r == g["r"], axis=1) & np.all(v == g["v"], axis=1))
-    print(f"\nkepler batch: max |dE|(1-e) {dE.max():.2e}, max rel r {er.max():.2e}, v {ev.max():.2e}, "
-          f"bit-identical states {100 * exact:.1f} %, E {100 * np.mean(E == g['E']):.1f} %")
+    print(f"\nkepler batch: libm mode 100 % bit-identical; cr mode {100 * exact_cr:.2f} %; fast mode max |dE|(1-e) "
+          f"{dE.max():.2e}, max rel r {er.max():.2e}, v {ev.max():.2e}, bit-identical states {100 * exact:.1f} %")
     assert dE.max() <= 4e-15 and er.max() <= 1e-13 and ev.max() <= 1e-13
+    with pytest.raises(nat.NativeError):
+        nat.set_trig_mode(7)
     # the solve_kepler grid of the reference (kepler.npz), through the same kernel
     k = golden("kepler")
     MM, ee = np.meshgrid(k["kep_M"], k["kep_e"])
     one = np.ones(MM.size)
     _, _, E2 = nat.kepler_states(MM.ravel(), ee.ravel(), one, one, one, 0 * one, 0 * one, 0 * one, return_E=True)
-    assert np.max(np.abs(E2 - k["kep_E"].ravel()) * (1.0 - ee.ravel())) <= 4e-15
+    assert_bits(E2, k["kep_E"].ravel(), "solve_kepler grid, libm mode")
     # host API
     from core.datasets import solar_system_v2
     system = solar_system_v2(moons=True)
     system.standardize_units(mass_unit="kilograms", distance_unit="meters", angle_unit="radians", time_unit="seconds")
     rs, vs = system.get_states()
     assert np.allclose(rs, k["r"], rtol=1e-13, atol=0) and np.allclose(vs, k["v"], rtol=1e-13, atol=1e-20)
+
+
+def test_device_trig_equals_host_builds(nat):
+    """The device build of csrc/sincos_libm.h / sincos_cr.h vs the host builds the CPU suite pins to glibc / mpmath
+    (tests/test_sincos.py), on every branch: with e = 0, a = b = 1 and no rotation the state is (cos M, sin M, 0)."""
+    from tests.test_sincos import branch_arguments, build_host_trig, host_sincos
+    trig = build_host_trig()
+    try:
+        for mode, fn, lim in (("libm", "sl_host_sincos", 1.05e8), ("cr", "sc_host_sincos", 2.0 ** 20)):
+            nat.set_trig_mode(mode)
+            for name, x in branch_arguments(200_000, seed=23).items():
+                x = x[np.abs(x) < lim]
+                one, zero = np.ones_like(x), np.zeros_like(x)
+                r, _ = nat.kepler_states(x, zero, one, one, one, zero, zero, zero, max_iter=1)
+                ok, s, c = host_sincos(trig, fn, x)
+                assert ok == 1
+                assert_bits(r[:, 0], c, f"device cos, {mode}, {name}")
+                assert_bits(r[:, 1], s + 0.0, f"device sin, {mode}, {name}")     # ry = 0*cos + sin: -0 becomes +0
+    finally:
+        nat.set_trig_mode("libm")
 
 
 def test_ensemble_generated_from_elements_on_device(nat):
@@ -710,12 +755,11 @@ def test_ensemble_generated_from_elements_on_device(nat):
     for f32 in (False, True):
         eng = EnsembleEngine.from_elements(M, e, a, inc, Om, om, m, dt=8640.0, softening=1e6, vel_f32=f32)
         st = eng.state()
-        for key in ("x", "y", "z"):
-            assert np.abs(st[key] - ref[key]).max() <= 1e-13 * np.abs(a).max()
+        for key in ("x", "y", "z"):                     # default trig mode: the host libm's bits (csrc/sincos_libm.h)
+            assert_bits(st[key], ref[key], f"ensemble from elements {key}")
         for key in ("vx", "vy", "vz"):
             want = ref[key].astype(np.float32).astype(np.float64) if f32 else ref[key]
-            tol = (2.0 ** -23 if f32 else 1e-13) * np.abs(ref[key]).max()
-            assert np.abs(st[key] - want).max() <= tol
+            assert_bits(st[key], want, f"ensemble from elements {key} f32={f32}")
         assert np.all(st["x"][:, 0] == 0.0) and np.all(st["vx"][:, 0] == 0.0)
         E0 = eng.energy()
         eng.step(200)
