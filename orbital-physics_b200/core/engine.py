@@ -15,6 +15,13 @@ re-uploaded before the next step.  Contacts are detected in the force pass and
 resolved with the reference's sequential semantics -- on the device by default
 (`contacts="device"`), or by the host replay (`contacts="host"`).
 
+Single `step()` calls are DEFERRED: a step that nothing can observe only bumps a counter, and the device runs the
+whole stretch in one launch when something looks (an attribute read or write of a bound object, `history`, `acc`,
+the diagnostics, a JSONL frame, `run()`, a changed parameter or membership, `close()`).  The reference's own
+driver loops -- `for _ in range(k): engine.step()` (core/examples.py:198-217) -- therefore cost one launch per
+stretch instead of one launch + one device round trip per step (25 us -> ~1 us per step at N = 15); the results are
+the same bits because the same steps run in the same order.  `ORBITAL_B200_DEFER=0` runs every step at once.
+
 `devices=` spreads one system over several GPUs (core/distributed.py): the
 same engine object, `run()`, `history`, diagnostics and JSONL frames on top of
 a `ShardedSystem` instead of a single `DeviceSystem`.
@@ -27,6 +34,7 @@ are *not* recomputed after a collision or an external mutation.
 from __future__ import annotations
 
 import json
+import operator
 import os
 import threading
 from collections.abc import Mapping
@@ -39,6 +47,8 @@ from core.physics import Coordinates, ObjectCollection, default_device, select_m
 
 _RING_BYTES = int(os.environ.get("ORBITAL_B200_HISTORY_BYTES", str(256 << 20)))
 _HOST_DIAG_MAX = 4096      # up to this many bodies diagnostics use the reference's NumPy expressions
+_DEFER = os.environ.get("ORBITAL_B200_DEFER", "1") != "0"
+_DEFER_MAX = 4096          # deferred steps are flushed at the latest when this many have piled up
 
 
 class _HistoryView(Mapping):
@@ -120,6 +130,7 @@ class SimulationEngine:
         self._snap = None               # host copy of what the device holds (SoA), refreshed by _pull
         self._pull_epoch = 0            # bumped by every _pull; an Object is current iff its _stamp equals it
         self._device_ahead = False
+        self._pending = 0               # step() calls not yet run on the device (see _flush)
         self._touched = {}              # slot -> Object materialised / written since the last host->device sync
         self._watch = {}                # slot -> Object whose velocity ndarray was handed out (may be edited in place)
         self._host_dirty = False
@@ -293,6 +304,7 @@ class SimulationEngine:
 
     def _pull(self):
         """Device -> host snapshot (one transfer); objects follow lazily."""
+        self._flush()
         st = self._dev.download_state()
         s = self._snap
         s["pos"] = np.stack([st["x"], st["y"], st["z"]])
@@ -304,6 +316,7 @@ class SimulationEngine:
 
     def _push_if_needed(self):
         """Host -> device if a touched object differs from the last synchronised snapshot."""
+        self._flush()                        # deferred steps were asked for before whatever changed
         objs = self.objects.objects
         if len(objs) != len(self._bound) or any(a is not b for a, b in zip(objs, self._bound)):
             if self._device_ahead:
@@ -348,6 +361,7 @@ class SimulationEngine:
 
     # ------------------------------------------------------------------ history
     def _hist_len(self):
+        self._flush()
         limit = self._hist_limit()
         return self._hist_total if limit is None else min(limit, self._hist_total)
 
@@ -365,6 +379,7 @@ class SimulationEngine:
     def _history_array(self):
         """[T, n, 3] of the retained points, oldest first (cached until the next append)."""
         with self._lock:
+            self._flush()
             key, arr = self._hist_cache
             if key == self._hist_total and arr is not None:
                 return arr
@@ -424,6 +439,7 @@ class SimulationEngine:
     def acc(self):
         """uuid -> acceleration (np.ndarray(3)) from the last force build."""
         with self._lock:
+            self._flush()
             ver, cached = self._acc_cache
             if ver == self._force_version and cached is not None:
                 return cached
@@ -435,11 +451,13 @@ class SimulationEngine:
     @acc.setter
     def acc(self, value):
         with self._lock:
+            self._flush()
             a = np.array([np.asarray(value[u], dtype=np.float64) for u in self._uuids]).T
             self._dev.upload_acc(np.ascontiguousarray(a))
             self._acc_cache = (self._force_version, dict(value))
 
     def _potential(self):
+        self._flush()
         ver, U = self._U_cache
         if ver == self._force_version and U is not None:
             return U
@@ -456,6 +474,7 @@ class SimulationEngine:
     @last_potential.setter
     def last_potential(self, value):
         with self._lock:
+            self._flush()
             self._U_cache = (self._force_version, value)
 
     # ------------------------------------------------------------------- stepping
@@ -478,11 +497,8 @@ class SimulationEngine:
             o._vel_seen = self._vel_key(o)
         self._dev.history_append()                  # engine.py:88-92 runs after the collision sweep
 
-    def _advance(self, nsteps: int):
-        """nsteps complete steps (engine.py:69-92), all on the device unless a contact halts it."""
-        self._push_if_needed()
-        if self._dev is None:
-            return
+    def _run_device(self, nsteps: int):
+        """nsteps steps on the device as it is bound and parametrised right now (no host -> device sync)."""
         left = int(nsteps)
         while left > 0:
             chunk = left
@@ -504,6 +520,33 @@ class SimulationEngine:
                 self._resolve_contacts()
             elif done < chunk:
                 raise RuntimeError("device stopped early without reporting a contact")
+
+    def _flush(self):
+        """Run the step() calls that were deferred.  While steps are pending nothing on the host is touched or
+        dirty (any access flushes first), so they run on the binding and the parameters they were asked for."""
+        k = self._pending
+        if k:
+            self._pending = 0
+            self._run_device(k)
+
+    def _can_defer(self):
+        """A step() that nothing can observe yet: same members, same parameters, no host-side edits to upload, no
+        velocity array handed out (the reference updates those in place every step), one process, one GPU."""
+        if not _DEFER or self._dev is None or self._devices is not None:
+            return False
+        if self._watch or self._touched or self._host_dirty:
+            return False
+        objs = self.objects.objects
+        if len(objs) != len(self._bound) or not all(map(operator.is_, objs, self._bound)):
+            return False
+        return (float(self.dt), float(self.softening), float(self._G), float(self.restitution)) == self._params
+
+    def _advance(self, nsteps: int):
+        """nsteps complete steps (engine.py:69-92), all on the device unless a contact halts it."""
+        self._push_if_needed()
+        if self._dev is None:
+            return
+        self._run_device(nsteps)
         if self._watch:
             self._pull()                # velocity arrays that were handed out track the state, as in the reference
 
@@ -516,7 +559,13 @@ class SimulationEngine:
 
     def step(self):
         with self._lock:
-            self._advance(1)
+            if self._can_defer():
+                if self._pending >= _DEFER_MAX:
+                    self._flush()
+                self._pending += 1
+                self._device_ahead = True       # the mirrors are behind: the next read pulls, and the pull flushes
+            else:
+                self._advance(1)
             self._tick()
 
     def run(self, steps: int):
@@ -617,11 +666,13 @@ class SimulationEngine:
     # ---------------------------------------------------------------------- misc
     def synchronize(self):
         with self._lock:
+            self._flush()
             if self._dev is not None:
                 self._dev.synchronize()
 
     def kernel_info(self) -> dict:
         with self._lock:
+            self._flush()
             return self._dev.force_kernel_info()
 
     def close(self):

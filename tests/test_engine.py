@@ -425,3 +425,80 @@ def test_massless_and_coincident_bodies(backend, orc):
     pos = np.array([o.position() for o in objs]); vel = np.array([o.velocity for o in objs])
     assert np.array_equal(pos, st.pos) and np.array_equal(vel, st.vel)
     assert np.isfinite(pos).all()
+
+
+@pytest.mark.parametrize("name", ["solar15_f32", "coll_dense_mixed"])
+@pytest.mark.parametrize("contacts", ["device", "host"])
+def test_deferred_steps_equal_immediate_steps(backend, golden, monkeypatch, name, contacts):
+    """step() calls that nothing observes are deferred and run as ONE device stretch when something looks
+    (the reference's driver loops call engine.step() once per step, core/examples.py:198-217).  Same steps in the
+    same order: every observable -- positions, velocities, accelerations, history, clock, JSONL-free run -- has the
+    same bits as with ORBITAL_B200_DEFER=0, across a parameter change, a host-side write and (coll_dense_mixed)
+    contacts resolved on the device or by the host replay; and the device is entered a handful of times, not 75."""
+    import core.engine as ce
+    from core.physics import Coordinates
+    g = golden(name)
+
+    def drive(defer):
+        monkeypatch.setattr(ce, "_DEFER", defer)
+        eng = build_engine(g, contacts=contacts)
+        objs = eng.objects.objects
+        calls = []
+        real = eng._dev.step
+        def counted(k):
+            r = real(k)
+            calls.append(int(r[0]))                         # steps completed by this entry into the device
+            return r
+        eng._dev.step = counted
+        seen = []
+        look = lambda: seen.append(np.array([[o.coordinates.x, o.coordinates.y, o.coordinates.z] for o in objs]))
+        for _ in range(40):
+            eng.step()
+        look()                                              # a read: runs the 40 steps
+        eng.dt = eng.dt * 0.5                               # parameter change: later steps only
+        for _ in range(25):
+            eng.step()
+        c = objs[2].coordinates                             # read + host-side write of one body
+        objs[2].coordinates = Coordinates(c.x * (1 + 1e-9), c.y, c.z)
+        for _ in range(10):
+            eng.step()
+        seen.append(np.array([eng.acc[o.uuid] for o in objs]))
+        look()
+        seen.append(np.array([eng._peek_velocity(o) for o in objs], dtype=np.float64))
+        seen.append(np.array([eng.history[o.uuid] for o in objs]))
+        seen.append(np.array([eng.last_potential, eng.total_energy(), eng.time_elapsed, eng.step_idx], dtype=np.float64))
+        eng.close()
+        return seen, calls
+
+    want, calls_now = drive(False)
+    got, calls_deferred = drive(True)
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert_bits(a, b, f"observable {k}")
+    assert sum(calls_now) == sum(calls_deferred) == 75
+    assert len(calls_now) >= 75
+    if contacts == "device" or name == "solar15_f32":
+        assert calls_deferred == [40, 1, 24, 1, 9], calls_deferred
+    else:
+        assert len(calls_deferred) < len(calls_now)
+
+
+def test_deferred_steps_cap_and_membership(backend, golden, monkeypatch):
+    """Deferred steps pile up to _DEFER_MAX at most; a body added between steps still raises KeyError in step()
+    like the reference (core/engine.py:70), after the steps that were asked for before it have run."""
+    import core.engine as ce
+    from core.physics import Coordinates, Object
+    g = golden("solar9_f32")
+    monkeypatch.setattr(ce, "_DEFER_MAX", 16)
+    eng = build_engine(g)
+    calls = []
+    real = eng._dev.step
+    eng._dev.step = lambda k: (calls.append(int(k)), real(k))[1]
+    for _ in range(40):
+        eng.step()
+    assert calls == [16, 16] and eng._pending == 8
+    eng.objects.append(Object(mass=1.0, radius=0.0, velocity=np.zeros(3), coordinates=Coordinates(1e13, 0.0, 0.0),
+                              angular_velocity=np.zeros(3), name="late"))
+    with pytest.raises(KeyError):
+        eng.step()
+    assert calls == [16, 16, 8]
+    eng.close()
