@@ -36,6 +36,7 @@ from __future__ import annotations
 import json
 import operator
 import os
+import sys
 import threading
 from collections.abc import Mapping
 
@@ -541,12 +542,21 @@ class SimulationEngine:
             return False
         return (float(self.dt), float(self.softening), float(self._G), float(self.restitution)) == self._params
 
+    def _prune_watch(self):
+        """Stop tracking velocity arrays nobody holds any more: once the caller has dropped the ndarray it got from
+        `obj.velocity` (reference count back to the attribute's own), no in-place edit can arrive through it and no
+        one can see it lag, so the object returns to the lazy path (edits made while it was held are in _touched)."""
+        for slot in [s for s, o in self._watch.items() if sys.getrefcount(o._velocity) <= 2]:
+            del self._watch[slot]
+
     def _advance(self, nsteps: int):
         """nsteps complete steps (engine.py:69-92), all on the device unless a contact halts it."""
         self._push_if_needed()
         if self._dev is None:
             return
         self._run_device(nsteps)
+        if self._watch:
+            self._prune_watch()
         if self._watch:
             self._pull()                # velocity arrays that were handed out track the state, as in the reference
 

@@ -502,3 +502,35 @@ def test_deferred_steps_cap_and_membership(backend, golden, monkeypatch):
         eng.step()
     assert calls == [16, 16, 8]
     eng.close()
+
+
+def test_velocity_array_is_tracked_only_while_it_is_held(backend, golden):
+    """An ndarray handed out by `obj.velocity` is the object's live array (the reference kicks it in place,
+    core/engine.py:70): it follows every step and an in-place edit reaches the device.  Once the caller drops it the
+    object goes back to the lazy / deferred path -- reading a velocity once does not cost a download per step for
+    the rest of the run."""
+    g = golden("solar9_f64")
+    ref = build_engine(g)
+    eng = build_engine(g)
+    calls = []
+    real = eng._dev.step
+    eng._dev.step = lambda k: (calls.append(int(k)), real(k))[1]
+    v = eng.objects.objects[3].velocity
+    rv = ref.objects.objects[3].velocity
+    for _ in range(3):
+        eng.step(); ref.step()
+        assert_bits(v, rv, "held array follows the state")
+    v += 1.0e-3                                            # in-place edit through the kept reference
+    rv += 1.0e-3
+    del v
+    eng.step(); ref.step()                                 # uploads the edit, then notices nobody holds the array
+    assert not eng._watch and calls == [1, 1, 1, 1]
+    for _ in range(20):
+        eng.step(); ref.step()
+    assert calls == [1, 1, 1, 1]                           # deferred again ...
+    assert_bits(eng.objects.objects[3].coordinates.x, ref.objects.objects[3].coordinates.x, "after release")
+    assert calls == [1, 1, 1, 1, 20]                       # ... and run as one stretch by the read
+    p1, v1, a1 = state_of(eng)
+    p2, v2, a2 = state_of(ref)
+    assert_bits(p1, p2, "pos"); assert_bits(v1, v2, "vel"); assert_bits(a1, a2, "acc")
+    eng.close(); ref.close()
