@@ -17,6 +17,8 @@ Extra records in the same JSON line (none of them changes `value`):
   scale_denominator  (N=1) a few timed steps at N=2,097,152 on one GPU: the denominator of the 2/4/8-GPU efficiency
   strong_262144      (N>1) the same N=262,144 workload as the 1-GPU line, spread over the ranks
   comm_ms            (N>1) mean CUDA-event time of the two collectives per step
+  ic_pipeline        (N=1) orbital elements -> states on the device (262,144 bodies) and a live bit-for-bit check against
+                     the unmodified reference's Body.get_state
   configs            (N=1) BASELINE configs[0] (solar system, 10,000 steps in one launch) and configs[1] (disk N=4,096)
   ensemble           BASELINE configs[3]
   cpu_baseline       the oracle port on all host threads + the UNMODIFIED Python reference (baseline/_ref) on 1 core
@@ -312,6 +314,37 @@ def parity_rows(orc, state, acc3n, m, eps, G, rows=64, seed=7):
     rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
     return {"rows": int(len(idx)), "max_rel": float(rel.max()), "tolerance": 1e-12,
             "oracle": "oracle/nbody_oracle.c row sums in the reference's order (core/physics.py:125-159)"}
+
+
+# --------------------------------------------------------------------------- initial-condition pipeline (N=1 only)
+def ic_pipeline(device, count=262144, live=512):
+    """orbital elements -> Cartesian states on the device (orb_kepler_states, csrc/kepler.cu) with the
+    host libm's sin / cos restated for the device, and the UNMODIFIED reference's Body.get_state (core/body.py:184-249)
+    on `live` random bodies in a subprocess: the device must reproduce its states bit for bit."""
+    from core import _native
+    rng = np.random.default_rng(99)
+    a = np.exp(rng.uniform(np.log(0.1), np.log(40.0), count)) * 1.495978707e11
+    e = rng.uniform(0.0, 0.95, count)
+    el = [rng.uniform(0.0, 2 * np.pi, count), e, a, a * np.sqrt(1 - e * e), np.sqrt(1.32712440018e20 / a ** 3),
+          np.abs(rng.normal(0.0, 0.3, count)), rng.uniform(0.0, 2 * np.pi, count), rng.uniform(0.0, 2 * np.pi, count)]
+    _native.kepler_states(*[x[:1024] for x in el], device=device)            # warm-up
+    t0 = time.perf_counter()
+    _native.kepler_states(*el, device=device)
+    dt = time.perf_counter() - t0
+    out = {"what": "orb_kepler_states: host arrays in, states out (copies and the host pow() pass included)",
+           "bodies": count, "ms": 1e3 * dt, "us_per_body": 1e6 * dt / count, "trig_mode": "libm (glibc restated)"}
+    ref = ref_timing("--case", "kepler", "--n", str(live))
+    if "r" in ref:
+        cols = [np.array(ref["elements"][k]) for k in ("M", "e", "a", "b", "n", "inc", "Omega", "omega")]
+        r, v = _native.kepler_states(*cols, device=device)
+        out["live_reference_check"] = {
+            "bodies": live, "bit_exact_positions": bool(np.array_equal(r, np.array(ref["r"]))),
+            "bit_exact_velocities": bool(np.array_equal(v, np.array(ref["v"]))),
+            "reference_us_per_body": ref["us_per_body"], "speedup_vs_reference": ref["us_per_body"] / out["us_per_body"],
+            "what": "unmodified reference Body.get_state (baseline/_ref, subprocess, 1 core) vs the device pipeline"}
+    else:
+        out["live_reference_check"] = ref
+    return out
 
 
 # --------------------------------------------------------------------------- small configs (N=1 only)
@@ -707,6 +740,10 @@ def run_ours(args):
             line["configs"] = small_configs(torch, local)
         except Exception as exc:
             line["configs"] = {"error": repr(exc)}
+        try:
+            line["ic_pipeline"] = ic_pipeline(local)
+        except Exception as exc:
+            line["ic_pipeline"] = {"error": repr(exc)}
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_sample(n, cloud, args.cpu_seconds)
         cb["note"] = ("C port of the reference algorithm on all host threads (kind: port). The reference itself is "

@@ -14,5 +14,7 @@ print(d["configs"]["C0_solar_system"]["live_reference_check"])
 print(d["configs"]["C1_disk_4096"]["runs"])
 print(d["ensemble"])
 r = json.load(open("gpurun_out/r2_bench_reference_arm.json"))
+print(d["ic_pipeline"])
+print("step() loop us/step:", [r.get("step_call_loop_us_per_step") for r in d["configs"]["C0_solar_system"]["runs"]])
 print("reference arm", r["value"], r["cpu_baseline"]["cores"])
 PY
