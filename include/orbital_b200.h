@@ -188,6 +188,12 @@ int orb_launch_count(orb_engine* e, int64_t* launches);
 /* U = -sum_{i<j} G m_i m_j / sqrt(r^2+eps^2)  (core/physics.py:158; last_potential).
  * Faithful mode and n <= 4096: lexicographic sequential order (bit-exact). */
 int orb_potential(orb_engine* e, double* U);
+/* Potential term of Object.lagrangian (core/physics.py:275-279) for one body:
+ * pe = sum_{j != body, ascending j} ((-G m_body) m_j) / ||r_body - r_j||, unsoftened, added in the
+ * reference's loop order (bit-identical to the Python loop; a coincident body gives -inf as there).
+ * G is the caller's (Object.unit_profile.G). The positions are the resident ones (all n bodies; on a
+ * sharded engine every rank holds them after a step). Synchronous. */
+int orb_body_potential(orb_engine* e, int64_t body, double G, double* pe);
 /* K = sum 1/2 m v.v, L = sum r x (m v)  (core/engine.py:104-121), fp64 tree reduction. */
 int orb_energy_angmom(orb_engine* e, double* K, double* L3);
 

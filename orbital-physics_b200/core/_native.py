@@ -78,6 +78,7 @@ SIGNATURES = {
     "orb_force_kernel_info": (C.c_int, [_vp, C.c_char_p, C.c_int, _intp, _intp, _intp, _intp]),
     "orb_launch_count": (C.c_int, [_vp, _i64p]),
     "orb_potential": (C.c_int, [_vp, _dblp]),
+    "orb_body_potential": (C.c_int, [_vp, C.c_int64, C.c_double, _dblp]),
     "orb_energy_angmom": (C.c_int, [_vp, _dblp, _f64]),
     "orb_history_count": (C.c_int, [_vp, _i64p]),
     "orb_history_append": (C.c_int, [_vp]),
@@ -372,6 +373,12 @@ class DeviceSystem:
     def potential(self) -> float:
         u = C.c_double()
         check(lib().orb_potential(self._h, C.byref(u)))
+        return u.value
+
+    def body_potential(self, body: int, G: float) -> float:
+        """Potential term of Object.lagrangian for one body, reference order (orb_body_potential)."""
+        u = C.c_double()
+        check(lib().orb_body_potential(self._h, int(body), float(G), C.byref(u)))
         return u.value
 
     def energy_angmom(self):

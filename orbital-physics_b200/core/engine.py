@@ -629,6 +629,20 @@ class SimulationEngine:
                 K += 0.5 * obj.mass * v2
             return K + self.last_potential
 
+    def _body_potential(self, obj, system, G):
+        """Potential term of `obj.lagrangian(system)` on the device (orb_body_potential: the reference's loop order,
+        core/physics.py:275-279), or None when `system` is not exactly this engine's bodies in their order (the
+        caller then runs the host loop, which reads the lazy mirrors)."""
+        with self._lock:
+            if self._dev is None or not hasattr(self._dev, "body_potential") or len(self._bound) < 16:
+                return None
+            if system is not self.objects and system is not self.objects.objects:
+                return None
+            self._push_if_needed()               # deferred steps, host-side edits, membership
+            if obj._engine is not self:
+                return None
+            return self._dev.body_potential(obj._slot, float(G))
+
     def angular_momentum(self):
         with self._lock:
             if len(self._bound) > _HOST_DIAG_MAX:

@@ -244,9 +244,17 @@ class Object:
         return f"Object({self.to_dict()})"
 
     def lagrangian(self, system: Iterable["Object"]) -> float:
-        """Kinetic (translation + spin) minus potential energy of this body in `system`."""
+        """Kinetic (translation + spin) minus potential energy of this body in `system`.
+
+        For a body bound to an engine and `system` = that engine's collection the O(N) potential loop runs on the
+        device in the same order (orb_body_potential, bit-identical); anything else takes the loop below."""
         T = 0.5 * self.mass * np.linalg.norm(self.velocity) ** 2
         T += 0.5 * self.moi * np.linalg.norm(self.angular_velocity) ** 2
+        eng = self._engine
+        if eng is not None:
+            pe = eng._body_potential(self, system, self.unit_profile.G)
+            if pe is not None:
+                return T - np.float64(pe)        # the host loop's pe is an np.float64 (T may be float32: NEP 50)
         here = self.coordinates.to_array()
         pe = 0
         for other in system:

@@ -869,6 +869,18 @@ int orb_potential(orb_engine* e, double* U) {
     return ORB_OK;
 }
 
+int orb_body_potential(orb_engine* e, int64_t body, double G, double* pe) {
+    LOCK(e);
+    if (!pe) return fail(ORB_ERR_INVALID, "null pe");
+    if (body < 0 || body >= e->s.n) return fail(ORB_ERR_INVALID, "body index out of range");
+    CU(launch_body_potential(e->s, body, G, e->d_diag, e->stream));
+    e->launches += 1;
+    CU(cudaMemcpyAsync(e->h_diag, e->d_diag, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *pe = e->h_diag[0];
+    return ORB_OK;
+}
+
 int orb_energy_angmom(orb_engine* e, double* K, double* L3) {
     LOCK(e);
     int launches = 0;

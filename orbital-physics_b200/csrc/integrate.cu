@@ -752,6 +752,39 @@ cudaError_t launch_potential(const DeviceState& s, const StepParams& p, bool fai
     return cudaGetLastError();
 }
 
+// Potential energy of ONE body against all others, unsoftened, in the reference's loop order -- the potential term
+// of Object.lagrangian (physics.py:275-279):  pe = sum_{j != i, ascending} ((-G m_i) m_j) / ||r_i - r_j||  with
+// np.linalg.norm = sqrt(x.dot(x)).  The CTA forms 256 terms at a time, thread 0 adds them in order: the same bits as
+// the Python loop (a coincident body gives -inf, as there).
+__global__ void __launch_bounds__(256) body_potential_kernel(const double4* __restrict__ pos4, long long n, long long i,
+                                                             double G, double* out) {
+    __shared__ double terms[256];
+    const double4 pi = pos4[i];
+    const double gmi = __dmul_rn(-G, pi.w);
+    double pe = 0.0;
+    for (long long j0 = 0; j0 < n; j0 += 256) {
+        const long long j = j0 + threadIdx.x;
+        if (j < n && j != i) {
+            const double4 pj = pos4[j];
+            const double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
+            terms[threadIdx.x] = __ddiv_rn(__dmul_rn(gmi, pj.w), __dsqrt_rn(dot3_numpy(dx, dy, dz)));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int cnt = (int)min(256LL, n - j0);
+            for (int k = 0; k < cnt; ++k)
+                if (j0 + k != i) pe = __dadd_rn(pe, terms[k]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = pe;
+}
+
+cudaError_t launch_body_potential(const DeviceState& s, long long i, double G, double* d_out, cudaStream_t st) {
+    body_potential_kernel<<<1, 256, 0, st>>>(s.pos4, s.n, i, G, d_out);
+    return cudaGetLastError();
+}
+
 // K = sum 1/2 m v.v ; L = sum r x (m v)     (engine.py:104-121, fp64)
 __global__ void __launch_bounds__(256) energy_angmom_kernel(const double4* __restrict__ pos4,
                                                             const double* __restrict__ vel, long long n,

@@ -103,6 +103,8 @@ cudaError_t launch_pack(double4* pos4, const double* x, const double* y, const d
 cudaError_t launch_unpack(const double4* pos4, double* x, double* y, double* z, long long n, cudaStream_t st);
 cudaError_t launch_potential(const DeviceState& s, const StepParams& p, bool faithful_order, double* d_out,
                              cudaStream_t st, int* launches);
+// potential term of Object.lagrangian (physics.py:275-279) for body i, reference order, unsoftened
+cudaError_t launch_body_potential(const DeviceState& s, long long i, double G, double* d_out, cudaStream_t st);
 cudaError_t launch_energy_angmom(const DeviceState& s, double* d_out4, cudaStream_t st, int* launches);
 
 // ---- peak.cu ----

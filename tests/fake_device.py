@@ -149,6 +149,17 @@ class FakeDeviceSystem:
             return self.u_stash
         return self.orc.potential(s.x, s.y, s.z, s.m, self.eps, self.G)
 
+    def body_potential(self, body, G):
+        """orb_body_potential: the potential loop of the reference's Object.lagrangian (physics.py:275-279)."""
+        s = self.st
+        here = np.array([s.x[body], s.y[body], s.z[body]])
+        pe = 0
+        for j in range(len(s.m)):
+            if j != body:
+                r = np.linalg.norm(here - np.array([s.x[j], s.y[j], s.z[j]]))
+                pe += -G * float(s.m[body]) * float(s.m[j]) / r
+        return float(pe)
+
     def energy_angmom(self):
         s = self.st
         return s.kinetic(), s.angmom()

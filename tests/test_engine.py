@@ -534,3 +534,38 @@ def test_velocity_array_is_tracked_only_while_it_is_held(backend, golden):
     p2, v2, a2 = state_of(ref)
     assert_bits(p1, p2, "pos"); assert_bits(v1, v2, "vel"); assert_bits(a1, a2, "acc")
     eng.close(); ref.close()
+
+
+def test_lagrangian_potential_on_the_device(backend, golden):
+    """Object.lagrangian(engine.objects) (reference core/physics.py:243-283): the O(N) potential loop of an
+    engine-bound body runs on the device in the reference's order -- same bits as the host loop, before and after
+    steps, after a host-side edit; any other `system` argument still takes the host loop."""
+    from core.physics import Coordinates, Object
+    g = golden("solar26_f32")
+    eng = build_engine(g)
+    objs = eng.objects.objects
+
+    def host_value(o):                                   # the reference expression, on plain unbound copies
+        clones = [Object(mass=b.mass, radius=b.radius, velocity=np.array(b.velocity, copy=True),
+                         coordinates=Coordinates(b.coordinates.x, b.coordinates.y, b.coordinates.z),
+                         angular_velocity=np.zeros(3), name=b.name) for b in objs]
+        return clones[objs.index(o)].lagrangian(clones)
+
+    calls = []
+    real = eng._dev.body_potential
+    eng._dev.body_potential = lambda i, G: (calls.append(i), real(i, G))[1]
+    for k in (0, 3, 25):                 # (body 0: the reference's float32 spin term overflows to nan -- kept)
+        assert_bits(objs[k].lagrangian(eng.objects), host_value(objs[k]), f"L[{k}] at t=0")
+    assert np.isfinite(objs[3].lagrangian(eng.objects)) and np.isfinite(objs[25].lagrangian(eng.objects))
+    for _ in range(7):
+        eng.step()
+    assert_bits(objs[9].lagrangian(eng.objects.objects), host_value(objs[9]), "L[9] after 7 steps")
+    c = objs[4].coordinates
+    objs[4].coordinates = Coordinates(c.x * 1.25, c.y, c.z)           # host-side edit reaches the device first
+    assert_bits(objs[9].lagrangian(eng.objects), host_value(objs[9]), "L[9] after an edit")
+    assert np.isfinite(objs[9].lagrangian(eng.objects))
+    assert calls == [0, 3, 25, 3, 25, 9, 9, 9]
+    assert_bits(objs[9].lagrangian(list(objs)), host_value(objs[9]), "host loop for a foreign iterable")
+    assert_bits(objs[9].lagrangian(objs[:12]), objs[9].lagrangian(iter(objs[:12])), "subset: host loop")
+    assert calls == [0, 3, 25, 3, 25, 9, 9, 9]
+    eng.close()
