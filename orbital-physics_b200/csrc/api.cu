@@ -833,7 +833,7 @@ int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, in
         }
     } else {
         const bool two_pass = faithful_pairs_applicable(e->s.n, e->sharded) && !e->pairs_unavailable;
-        nm = two_pass ? "faithful_pairs_kernel+faithful_rows_kernel" : "force_faithful_kernel";
+        nm = two_pass ? faithful_two_pass_name(e->s.n) : "force_faithful_kernel";
         faithful_geometry(e->s.tgt_hi - e->s.tgt_lo, &g, &b);
         sm = b * 40;
         if (two_pass) lps = (e->p.device_contacts && e->detect) ? 5 : 3;     // step tail fused into pass 2

@@ -852,6 +852,23 @@ bool faithful_pairs_applicable(long long n, bool sharded) {
     return !sharded && n > tiny_limit() && n <= 32768;               // 8 n^2 bytes of scratch: 8 GiB at n = 32768
 }
 
+// pass-2 kernel of the two-pass path: 2 = producer / consumer warps (default up to 148 column blocks), 1 = one warp
+// per 32 targets (default above), 4 = four lanes per target (ORBITAL_B200_ROWS selects; read per call)
+static int faithful_rows_variant(long long n) {
+    const char* rows_env = getenv("ORBITAL_B200_ROWS");
+    const int v = rows_env ? atoi(rows_env) : 2;
+    if (v == 4 || v == 1) return v;
+    return (n + 31) / 32 <= 148 ? 2 : 1;
+}
+
+const char* faithful_two_pass_name(long long n) {
+    switch (faithful_rows_variant(n)) {
+        case 4: return "faithful_pairs_kernel+faithful_rows4_kernel";
+        case 2: return "faithful_pairs_kernel+faithful_rows2_kernel";
+        default: return "faithful_pairs_kernel+faithful_rows_kernel";
+    }
+}
+
 long long faithful_pairs_ld(long long n) { return (n + 31) / 32 * 32; }
 long long faithful_pairs_elems(long long n) { return faithful_pairs_ld(n) * faithful_pairs_ld(n); }
 
@@ -906,9 +923,7 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
         //   N      rows2   rows1   rows4          N       rows2*  rows1   rows4      (* falls back to rows1 above 148 blocks)
         //   1,024   27.1    29.9    46.1          8,192    297.9   297.6   524.8
         //   4,096  107.5   119.0   186.5         16,384    900.6   899.7  1984.7
-        const char* rows_env = getenv("ORBITAL_B200_ROWS");
-        const int rows_variant = rows_env ? atoi(rows_env) : 2;
-        const bool one_warp_rows = rows_variant == 1;
+        const int rows_variant = faithful_rows_variant(s.n);
         if (rows_variant == 4) {
             static DeviceOnce rows4_attr;
             if (rows4_attr.first()) {
@@ -923,7 +938,7 @@ static void launch_faithful_t(const DeviceState& s, const StepParams& p, bool de
                                                                        tail);
             return;
         }
-        if (!one_warp_rows && rows_variant == 2 && nb <= 148) {
+        if (rows_variant == 2) {
             static DeviceOnce rows2_attr;
             if (rows2_attr.first()) {
                 cudaFuncSetAttribute(faithful_rows2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2Smem);

@@ -77,6 +77,7 @@ void faithful_geometry(long long n_tgt, int* grid, int* block);
 // two-pass bit-exact force (pair matrix of 1/r^3, then ordered row sums): sizes it is used for, leading dimension
 bool faithful_pairs_applicable(long long n, bool sharded);
 long long faithful_pairs_ld(long long n);
+const char* faithful_two_pass_name(long long n);     // which pass-2 kernel the two-pass path runs at this size
 long long faithful_pairs_elems(long long n);
 const char* fast_kernel_name(int ti, bool detect);
 
