@@ -206,7 +206,8 @@ int orb_history_download(orb_engine* e, int64_t last_k, double* out, int64_t* go
 
 /* ---- batched ensemble: nsys independent systems of nbody bodies ---------
  * BASELINE config C3. Bit-exact mode: one warp per system; fast mode: nbody/2 lanes
- * per system, 64/nbody systems per warp. Arrays are [nsys][nbody] fp64.
+ * per system, 64/nbody systems per warp (small batches: one body per lane, nbody lanes
+ * per system -- twice the warps). Arrays are [nsys][nbody] fp64.
  * Equivalent to nsys separate SimulationEngine instances stepped in lockstep
  * (core/engine.py:19-46,65-97) without collision handling. */
 int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int mode, int vel_f32);

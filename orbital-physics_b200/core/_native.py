@@ -436,7 +436,7 @@ def kepler_states(M, e, a, b, n, inc, Omega, omega, tol: float = 1e-12, max_iter
 
 class DeviceEnsemble:
     """nsys independent systems of nbody bodies (orb_ens_*): one warp per system in bit-exact mode, nbody/2 lanes per
-    system (64/nbody systems per warp) in fast mode."""
+    system (64/nbody systems per warp) in fast mode -- nbody lanes per system for small batches."""
 
     def __init__(self, nsys: int, nbody: int, device: int = 0, mode: int = MODE_FAST, vel_f32: bool = False):
         self._h = _vp()

@@ -4,7 +4,7 @@ Semantically `nsys` separate reference `SimulationEngine`s (core/engine.py:19-46
 65-97 of the reference) advanced in lockstep -- including, when radii are given,
 the contact sweep every engine runs after its step (engine.py:85) and per-body
 velocity dtypes (physics.py:184 vs :448-449).  Bit-exact mode: one warp per
-system; fast mode: nbody/2 lanes per system, 64/nbody systems per warp.
+system; fast mode: nbody/2 lanes per system, 64/nbody systems per warp (small batches: nbody lanes per system).
 Systems are independent, so multi-GPU runs block-partition them with no
 collectives (`partition`).
 """

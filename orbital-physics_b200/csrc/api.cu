@@ -940,6 +940,8 @@ int orb_history_download(orb_engine* e, int64_t last_k, double* out, int64_t* go
 // ===========================================================================
 // Ensemble
 // ===========================================================================
+constexpr int kEnsNarrowBelow = 4;      // warps per SM sub-partition below which the fast kernel goes one body per lane
+
 struct orb_ensemble {
     std::mutex mu;
     int device = 0;
@@ -1106,6 +1108,11 @@ int orb_ens_create(orb_ensemble** out, int64_t nsys, int nbody, int device, int 
         // one warp per system; several systems share a CTA (measured: 1 -> 3.5 TB/s, >= 2 -> 4.1 TB/s)
         const char* env = getenv("ORBITAL_B200_ENS_WARPS");
         s->a.warps_per_cta = env ? atoi(env) : 4;
+        // fast mode: one body per lane when the two-body layout would leave fewer than kEnsNarrowBelow warps per SM
+        // sub-partition (ORBITAL_B200_ENS_NARROW = 0 | 1 forces it off / on)
+        env = getenv("ORBITAL_B200_ENS_NARROW");
+        const long long warps2 = (nsys * (long long)nbp + 63) / 64;
+        s->a.narrow = env ? (env[0] == '1') : (warps2 < (long long)kEnsNarrowBelow * 4 * std::max(1, s->sm_count));
     }
     s->a.dt = 1.0; s->a.h = 0.5; s->a.dt32 = 1.0f; s->a.eps2 = 0.0; s->a.G = 6.67430e-11;
     *out = s;
@@ -1301,7 +1308,8 @@ int orb_ens_step(orb_ensemble* s, int64_t nsteps, int fused) {
         a.nsteps = nsteps;
         a.first = a.last = 1;
         // few warps of work per SM sub-partition: balance them dynamically in time slices (bit-identical result)
-        const bool sliced = !faithful && s->slice > 0 && nsteps >= 2 * s->slice &&
+        const bool narrow = a.narrow && !a.radius;           // one body per lane: twice the warps, no slicing needed
+        const bool sliced = !faithful && !narrow && s->slice > 0 && nsteps >= 2 * s->slice &&
                             s->progress_len <= (long long)s->sm_count * 4 * 4;    // < 4 warps per SM sub-partition
         if (sliced) {
             CU(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), s->stream));

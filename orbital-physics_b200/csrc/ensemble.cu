@@ -398,6 +398,122 @@ __global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const 
                                    cb_all[DETECT ? warp : 0]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast mode, NARROW layout for small batches: ONE body per lane, NBP lanes per system, 32 / NBP systems per warp.
+// The two-body layout above needs 64 / NBP x fewer warps per system, which is what a big batch wants (fewer shuffles
+// and shared-memory loads per pair); a batch of 8,192 16-body systems (BASELINE configs[3] split over 8 GPUs) then
+// has only 3.5 warps per SM sub-partition and cannot hide its FP64 latency (r2a: 87 % of the full-batch rate even
+// with the time-sliced kernel).  Here the same batch is twice as many warps with half the work each: every unordered
+// pair still once -- ring offsets 1 .. NBP/2, the last one (antipodes) by the lower half only -- own accelerations
+// in the lane, reactions in a travelling accumulator that moves one lane per offset and goes home after the last
+// (3 SHFL and 2 LDS per pair instead of 1.5 and 1).  Same launch contract (first / last) and rounding of the
+// integrator as ens_fast_body; no contact handling (systems with radii take the two-body variant).
+template <int NBP, int VM>
+__device__ __forceinline__ void ens_fast_body1(const EnsArgs& g, long long sys0, long long nsteps, bool first,
+                                               bool last, double2* sxy_w, double* sz_w) {
+    constexpr int NS = NBP / 2;                  // ring offsets 1..NS
+    constexpr int LM = NBP - 1;
+    const int lane = threadIdx.x & 31;
+    const int I = lane & LM;
+    const int sw = lane / NBP;
+    const long long sys = sys0 + sw;
+    const int nb = g.nb;
+    double2* sxy = sxy_w + sw * NBP;
+    double* sz = sz_w + sw * NBP;
+    const bool has = sys < g.nsys && I < nb;
+    const long long o = sys * nb + I;
+    double x = 1e150 * (double)(I + 1), y = 0.0, z = 0.0, m = 0.0;       // padded slot: far away, massless
+    double vx = 0.0, vy = 0.0, vz = 0.0, ax = 0.0, ay = 0.0, az = 0.0;
+    bool f32 = VM == 1;
+    if (has) {
+        x = __ldcg(g.x + o); y = __ldcg(g.y + o); z = __ldcg(g.z + o); m = g.m[o];
+        vx = __ldcg(g.vx + o); vy = __ldcg(g.vy + o); vz = __ldcg(g.vz + o);
+        if (first) { ax = __ldcg(g.ax + o); ay = __ldcg(g.ay + o); az = __ldcg(g.az + o); }
+        if (VM == 2) f32 = g.vf32[o] != 0;
+    }
+    // partner masses do not change: fetch them once (through the z slots)
+    double mj[NS];
+    sz[I] = m;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const bool vt = (t + 1 < NS) || (I < NS);                        // the upper half skips the antipodes
+        mj[t] = vt ? sz[(I + t + 1) & LM] : 0.0;
+    }
+    const double mi_last = (I < NS) ? m : 0.0;                           // own mass as the antipodal offset sees it
+    __syncwarp();
+    const double h = g.h, dt = g.dt, G = g.G, eps2 = g.eps2;
+    const float dt32 = g.dt32;
+    const int group = lane & ~LM;
+    if (first && has) {
+        vx = ens_kick<VM>(vx, h, ax, f32);                               // engine.py:69-70
+        vy = ens_kick<VM>(vy, h, ay, f32);
+        vz = ens_kick<VM>(vz, h, az, f32);
+    }
+    for (long long s = 0; s < nsteps; ++s) {
+        if (has) {
+            x = ens_drift<VM>(x, vx, dt, dt32, f32);                     // engine.py:73-75
+            y = ens_drift<VM>(y, vy, dt, dt32, f32);
+            z = ens_drift<VM>(z, vz, dt, dt32, f32);
+        }
+        sxy[I] = make_double2(x, y);
+        sz[I] = z;
+        __syncwarp();
+        double a0x = 0.0, a0y = 0.0, a0z = 0.0;                          // own acceleration (physics.py:151)
+        double cx = 0.0, cy = 0.0, cz = 0.0;                             // travelling: reactions on body I + offset (:152)
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            const int J = (I + t + 1) & LM;
+            const double2 pxy = sxy[J];
+            const double pz = sz[J];
+            const double mi = (t + 1 == NS) ? mi_last : m;
+            const double dx = pxy.x - x, dy = pxy.y - y, dz = pz - z;
+            const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+            int hi;
+            const double s0 = inv_r3_plain(r2, hi);
+            const double si = s0 * mj[t], sj = s0 * mi;
+            a0x = fma(si, dx, a0x); a0y = fma(si, dy, a0y); a0z = fma(si, dz, a0z);
+            cx = fma(-sj, dx, cx); cy = fma(-sj, dy, cy); cz = fma(-sj, dz, cz);
+            // the next offset meets body I + t + 2, whose accumulator sits one lane up; after the last offset the
+            // accumulator of body I + NS goes home
+            const int src = group | ((t + 1 < NS ? I + 1 : I - NS) & LM);
+            cx = __shfl_sync(0xffffffffu, cx, src);
+            cy = __shfl_sync(0xffffffffu, cy, src);
+            cz = __shfl_sync(0xffffffffu, cz, src);
+        }
+        ax = G * (a0x + cx); ay = G * (a0y + cy); az = G * (a0z + cz);
+        if (has) {
+            vx = ens_kick<VM>(vx, h, ax, f32);                           // engine.py:81-82
+            vy = ens_kick<VM>(vy, h, ay, f32);
+            vz = ens_kick<VM>(vz, h, az, f32);
+            if (s + 1 < nsteps || !last) {
+                vx = ens_kick<VM>(vx, h, ax, f32);                       // the next step's first half-kick
+                vy = ens_kick<VM>(vy, h, ay, f32);
+                vz = ens_kick<VM>(vz, h, az, f32);
+            }
+        }
+        __syncwarp();
+    }
+    if (has) {
+        g.x[o] = x; g.y[o] = y; g.z[o] = z;
+        g.vx[o] = vx; g.vy[o] = vy; g.vz[o] = vz;
+        if (last) { g.ax[o] = ax; g.ay[o] = ay; g.az[o] = az; }
+    }
+}
+
+template <int NBP, int VM>
+__global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast1_kernel(const EnsArgs g) {
+    constexpr int SPW = 32 / NBP;                // systems per warp
+    __shared__ double2 sxy_all[kEnsMaxWarps][32];
+    __shared__ double sz_all[kEnsMaxWarps][32];
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5;
+    const long long sys0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * SPW;
+    if (sys0 >= g.nsys) return;                  // whole warp exits together
+    pdl_wait();
+    ens_fast_body1<NBP, VM>(g, sys0, g.nsteps, g.first != 0, g.last != 0, sxy_all[warp], sz_all[warp]);
+}
+
 // Time-sliced variant for small batches in fused mode.  With only a few warps of work per SM sub-partition
 // (8,192 16-body systems = 3.46 warps per scheduler on 148 SMs) a static assignment leaves the schedulers that got
 // 3 warps idle a quarter of the time.  Here a fixed crew of warps (one CTA of 4 per SM slot) pulls (group of SPW
@@ -522,6 +638,10 @@ static void launch_ens_variant(const EnsArgs& a, int w, cudaStream_t st) {
     if (FAITHFUL) {
         cfg.gridDim = dim3((unsigned)((a.nsys + w - 1) / w));                   // one warp per system
         cudaLaunchKernelEx(&cfg, ens_step_kernel<NBP, VM, DETECT>, a);
+    } else if (!DETECT && a.narrow) {
+        const long long per_cta = (long long)w * (32 / NBP);                    // one body per lane
+        cfg.gridDim = dim3((unsigned)((a.nsys + per_cta - 1) / per_cta));
+        cudaLaunchKernelEx(&cfg, ens_step_fast1_kernel<NBP, VM>, a);
     } else {
         const long long per_cta = (long long)w * (64 / NBP);                    // 64/NBP systems per warp
         cfg.gridDim = dim3((unsigned)((a.nsys + per_cta - 1) / per_cta));

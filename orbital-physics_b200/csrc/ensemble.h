@@ -18,6 +18,7 @@ struct EnsArgs {
     unsigned long long* contacts;   // device counter: touching pairs resolved (or nullptr)
     int pdl;               // host only: launch with programmatic stream serialization (overlaps the predecessor's tail)
     int first, last;       // see ensemble.cu: does the launch start from / end with the synchronised (x, v, a) state
+    int narrow;            // fast mode without contacts: one body per lane (ens_fast_body1) instead of two
 };
 cudaError_t launch_ens_step(const EnsArgs& a, bool faithful, cudaStream_t st);
 // fast mode, all a.nsteps in one launch, balanced over the SMs in slices of `slice` steps (small batches)

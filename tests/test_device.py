@@ -488,13 +488,16 @@ def test_ensemble_faithful_bit_exact_and_fast_close(nat, orc):
     fast.close()
 
 
+@pytest.mark.parametrize("narrow", ["0", "1"])
 @pytest.mark.parametrize("nbody", [2, 5, 13, 16, 17, 32])
-def test_ensemble_fast_acceleration_within_tolerance_every_step(nat, orc, nbody):
-    """ens_step_fast_kernel: relative acceleration error <= 1e-12 per step (BASELINE north_star), checked on every
+def test_ensemble_fast_acceleration_within_tolerance_every_step(nat, orc, nbody, narrow, monkeypatch):
+    """ens_step_fast_kernel (two bodies per lane) and ens_step_fast1_kernel (one body per lane, the layout small
+    batches take): relative acceleration error <= 1e-12 per step (BASELINE north_star), checked on every
     body of 48 systems against the oracle at the SAME positions, after un-fused and fused steps, both velocity
     dtypes -- the ensemble keeps every system's engine.acc (orb_ens_download_acc)."""
     from core import synthetic
     from core.ensemble import EnsembleEngine
+    monkeypatch.setenv("ORBITAL_B200_ENS_NARROW", narrow)
     e = synthetic.ensemble(48, nbody)
     args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
     worst = 0.0
@@ -510,7 +513,7 @@ def test_ensemble_fast_acceleration_within_tolerance_every_step(nat, orc, nbody)
                 worst = max(worst, float(err.max()))
                 assert err.max() <= TOL_FAST, f"nbody={nbody} f32={vel_f32} system {s}: {err.max():.3e}"
         ens.close()
-    print(f"\nensemble fast kernel nbody={nbody}: max rel acceleration error {worst:.2e}")
+    print(f"\nensemble fast kernel nbody={nbody} narrow={narrow}: max rel acceleration error {worst:.2e}")
 
 
 def _ensemble_contact_scene(nsys, nb, seed):
@@ -575,6 +578,7 @@ def test_ensemble_time_sliced_fused_kernel_is_bit_identical(nat, monkeypatch, nb
     """Small batches in fused mode run ens_fast_sliced_kernel (work queue of (system group, 16-step slice) items,
     state handed over in its synchronised form): same bits as the single pass and as one launch per step."""
     from core import synthetic
+    monkeypatch.setenv("ORBITAL_B200_ENS_NARROW", "0")  # (small batches default to one body per lane, never sliced)
     e = synthetic.ensemble(301, nb)
     args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
     K = 117                                              # 7 slices of 16 + one of 5
@@ -592,6 +596,41 @@ def test_ensemble_time_sliced_fused_kernel_is_bit_identical(nat, monkeypatch, nb
         for k in st:
             assert_bits(st[k], outs[0][0][k], f"sliced vs single-pass {k}")
         assert_bits(acc, outs[0][1], "accelerations")
+
+
+@pytest.mark.parametrize("nb", [2, 3, 7, 16, 21, 32])
+def test_ensemble_one_body_per_lane_layout(nat, monkeypatch, nb):
+    """The narrow layout (ens_step_fast1_kernel: one body per lane, what a batch with fewer than 4 warps of work per
+    SM sub-partition takes by default): fused, one launch per step (incl. the 16-step graphs) and mixed calls give
+    the same bits; per-body velocity dtypes; padded slots and the ragged last warp contribute nothing; the
+    trajectories stay within 1e-10 of the two-body layout (which other tests hold to the oracle) over 40 steps."""
+    from core import synthetic
+    nsys = 203
+    e = synthetic.ensemble(nsys, nb)
+    args = [e[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
+    flags = (np.arange(nsys * nb).reshape(nsys, nb) % 3 == 0).astype(np.uint8)
+    vel = [np.where(flags, np.asarray(a, dtype=np.float32).astype(np.float64), a) for a in args[3:6]]
+    outs = []
+    for narrow, plan in (("1", ((40, True),)), ("1", ((40, False),)), ("1", ((7, False), (16, True), (17, False))),
+                         ("0", ((40, True),))):
+        monkeypatch.setenv("ORBITAL_B200_ENS_NARROW", narrow)
+        ens = nat.DeviceEnsemble(nsys, nb, 0, nat.MODE_FAST)
+        ens.set_params(e["dt"], e["eps"], e["G"])
+        ens.set_bodies(np.zeros((nsys, nb)), flags)
+        ens.upload(*args[:3], *vel, args[6])
+        for k, fused in plan:
+            ens.step(k, fused=fused)
+        outs.append((ens.download(), ens.download_acc()))
+        ens.close()
+    for st, acc in outs[1:3]:
+        for k in st:
+            assert_bits(st[k], outs[0][0][k], f"narrow layout, fused vs un-fused {k}")
+        assert_bits(acc, outs[0][1], "accelerations")
+    wide = outs[3][0]
+    for k in ("x", "y", "z"):
+        scale = np.abs(wide[k]).max()
+        assert np.all(np.isfinite(outs[0][0][k]))
+        assert np.abs(outs[0][0][k] - wide[k]).max() <= 1e-10 * scale, f"narrow vs two-body layout {k}"
 
 
 def test_ensemble_odd_sizes(nat, orc):
