@@ -722,7 +722,7 @@ def run_ours(args):
         "config": {"workload": name, "n_bodies": n, "mode": "fast", "ic": "Plummer (Aarseth-Henon-Wielen), seed=N",
                    "interactions_per_step": "N^2", "l2": "flushed between steps (256 MiB memset)",
                    "parallelism": "1 GPU" if world == 1 else
-                                  f"snake-order pair-block ownership x{world}, all-gather 32 B x N + reduce-scatter / all-reduce 24 B x N"},
+                                  f"snake-order pair-block ownership x{world}, all-gather 32 B x N (NCCL) + reduction of the partial accelerations out of peer memory (CUDA IPC over NVLink; NCCL fallback)"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity_check": parity,
     }

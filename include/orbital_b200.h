@@ -178,6 +178,20 @@ int orb_synchronize(orb_engine* e);
 int orb_pos4_ptr(orb_engine* e, void** device_ptr, int64_t* n_bodies);
 int orb_vel_ptr(orb_engine* e, void** device_ptr);   /* 3 x n fp64, SoA */
 int orb_acc_ptr(orb_engine* e, void** device_ptr);   /* 3 x n fp64, SoA */
+/* Peer-memory reduction of the partial accelerations (one process per GPU on one NVLink / NVSwitch node):
+ * instead of all-reducing orb_acc_ptr with NCCL, every rank exports its buffer (CUDA IPC handle + offset,
+ * orb_peer_export), opens every other rank's (orb_peer_open) and, after each force pass, sums the columns
+ * of ITS OWN slab straight out of peer memory in fixed rank order (orb_peer_reduce, asynchronous) -- the
+ * reduce-scatter the second half-kick needs, in one kernel over NVLink. The caller synchronises the ranks:
+ * all force passes are complete before any orb_peer_reduce (e.g. a 1-element all-reduce on the same
+ * stream), and no rank starts its next force pass before all have reduced (the position all-gather of the
+ * next step does that). Replaces the all-reduce of the reference-side multi-GPU plan. */
+int orb_peer_export(orb_engine* e, void* handle64, int64_t* offset);
+int orb_peer_open(orb_engine* e, int rank, const void* handle64, int64_t offset);
+int orb_peer_reduce(orb_engine* e);
+/* Unmap the other ranks' buffers (synchronises this handle's stream first). An exporting rank must not
+ * destroy its engine before every importer has closed: close on all ranks, barrier, then orb_destroy. */
+int orb_peer_close(orb_engine* e);
 /* Name and launch geometry of the force kernel the current mode/size selects. */
 int orb_force_kernel_info(orb_engine* e, char* name, int name_len, int* grid, int* block,
                           int* smem_bytes, int* launches_per_step);

@@ -75,6 +75,10 @@ SIGNATURES = {
     "orb_pos4_ptr": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
     "orb_vel_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
     "orb_acc_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "orb_peer_export": (C.c_int, [_vp, C.c_char_p, _i64p]),
+    "orb_peer_open": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int64]),
+    "orb_peer_reduce": (C.c_int, [_vp]),
+    "orb_peer_close": (C.c_int, [_vp]),
     "orb_force_kernel_info": (C.c_int, [_vp, C.c_char_p, C.c_int, _intp, _intp, _intp, _intp]),
     "orb_launch_count": (C.c_int, [_vp, _i64p]),
     "orb_potential": (C.c_int, [_vp, _dblp]),
@@ -356,6 +360,23 @@ class DeviceSystem:
         p = _vp()
         check(lib().orb_acc_ptr(self._h, C.byref(p)))
         return p.value
+
+    # -- peer-memory reduction of the partial accelerations (one process per GPU) --
+    def peer_export(self):
+        """(CUDA IPC handle: 64 bytes, offset of the acc buffer inside the exported allocation)."""
+        h = C.create_string_buffer(64)
+        off = C.c_int64()
+        check(lib().orb_peer_export(self._h, h, C.byref(off)))
+        return bytes(h.raw), int(off.value)
+
+    def peer_open(self, rank: int, handle: bytes, offset: int):
+        check(lib().orb_peer_open(self._h, int(rank), C.create_string_buffer(handle, 64), int(offset)))
+
+    def peer_reduce(self):
+        check(lib().orb_peer_reduce(self._h))
+
+    def peer_close(self):
+        check(lib().orb_peer_close(self._h))
 
     def force_kernel_info(self) -> dict:
         name = C.create_string_buffer(128)

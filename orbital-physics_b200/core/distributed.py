@@ -34,6 +34,8 @@ The reference has no distributed path; the per-step semantics are the reference'
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from core import _native
@@ -171,6 +173,7 @@ class ShardedSystem:
             self._bind_stream(dev)
         self.dev = self.devs[0]
         self._partial = bool(self.dev.acc_needs_allreduce()) and self.world > 1
+        self._peer = self._partial and self._open_peers()
         self._detect = False
         self._acc_full = True
         self._vel_full = True
@@ -188,6 +191,34 @@ class ShardedSystem:
         s.upload(x, y, z, vx, vy, vz, m, radius, vel_is_f32)
         s.accel()
         return s
+
+    def _open_peers(self) -> bool:
+        """One process per GPU over NCCL on one node: map the other ranks' acc buffers (CUDA IPC) so that the partial
+        accelerations are summed straight out of peer memory (orb_peer_reduce) instead of by an NCCL collective.
+        Every rank takes part in the two exchanges; the reduction is used only if it could be set up on ALL ranks
+        (ORBITAL_B200_PEER_REDUCE=0: never)."""
+        comm = self.comm
+        if not isinstance(comm, DistComm) or self.n != self.per * self.world or not hasattr(self.dev, "peer_export"):
+            return False
+        if os.environ.get("ORBITAL_B200_PEER_REDUCE", "1") == "0" or comm.dist.get_backend(comm.group) != "nccl":
+            return False
+        try:
+            mine = self.dev.peer_export()
+        except _native.NativeError:
+            mine = None
+        every = comm.all_gather_host([mine])
+        ok = all(h is not None for h in every)
+        if ok:
+            try:
+                for r, (handle, offset) in enumerate(every):
+                    if r != self.rank:
+                        self.dev.peer_open(r, handle, offset)
+            except _native.NativeError:
+                ok = False
+        ok = all(comm.all_gather_host([ok]))
+        if ok:
+            self._peer_flag = self.torch.zeros(1, device=f"cuda:{self.dev.device}")
+        return ok
 
     # -- backend seams (overridden by the CPU test double) ------------------
     def _make_device(self, rank, lo, hi):
@@ -305,7 +336,15 @@ class ShardedSystem:
         the total for its own slab only (what its half-kick reads); ragged slabs or small systems: all-reduce."""
         # measured on 2 x B200: N = 2,097,152 reduce-scatter (3 rows) 0.96 ms vs all-reduce 1.16 ms; N = 262,144
         # 0.41 vs 0.26 ms -- three latency-bound calls lose to one below ~1M bodies
-        if self._partial and self.n == self.per * self.world and self.n >= (1 << 20):
+        if self._peer:
+            def peer():
+                # every rank's force pass is complete before anyone reads peer memory (stream-ordered, no host sync);
+                # the next step's position all-gather keeps the next force pass behind everybody's reduction
+                self.comm.dist.all_reduce(self._peer_flag, group=self.comm.group)
+                self.dev.peer_reduce()
+            self._timed("reduce", peer)
+            self._acc_full = False
+        elif self._partial and self.n == self.per * self.world and self.n >= (1 << 20):
             self._timed("reduce", lambda: self.comm.reduce_scatter_rows(self._acc, self.per))
             self._acc_full = False
         elif self._partial:
@@ -421,6 +460,13 @@ class ShardedSystem:
         return self._partial
 
     def close(self):
+        """Collective when the ranks read each other's buffers (peer reduction): every importer unmaps, then a
+        barrier, and only then does any rank free the buffer it exported."""
+        if self._peer and self.devs:
+            self.dev.peer_close()
+            self.comm.dist.all_reduce(self._peer_flag, group=self.comm.group)
+            self.torch.cuda.synchronize()
+            self._peer = False
         for d in self.devs:
             d.close()
         self.devs = []

@@ -785,6 +785,30 @@ cudaError_t launch_body_potential(const DeviceState& s, long long i, double G, d
     return cudaGetLastError();
 }
 
+// Sum of the ranks' partial accelerations for this rank's slab, read from peer memory (see orb_peer_reduce).
+// Volatile loads: the addresses were read in the previous step too and nothing may be served from a stale line.
+struct PeerAcc { const double* p[16]; };
+__global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerAcc peers, int world, double* acc, long long n,
+                                                          long long lo, long long hi) {
+    const long long per = hi - lo;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= 3 * per) return;
+    const long long c = t / per;
+    const long long idx = c * n + lo + (t - c * per);
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += *reinterpret_cast<const volatile double*>(peers.p[r] + idx);   // rank order
+    acc[idx] = s;
+}
+
+cudaError_t launch_peer_reduce(const double* const* peer_acc, int world, double* acc, long long n, long long lo,
+                               long long hi, cudaStream_t st) {
+    PeerAcc pa{};
+    for (int r = 0; r < world && r < 16; ++r) pa.p[r] = peer_acc[r];
+    const long long tot = 3 * (hi - lo);
+    peer_reduce_kernel<<<grid_for(tot, 256), 256, 0, st>>>(pa, world, acc, n, lo, hi);
+    return cudaGetLastError();
+}
+
 // K = sum 1/2 m v.v ; L = sum r x (m v)     (engine.py:104-121, fp64)
 __global__ void __launch_bounds__(256) energy_angmom_kernel(const double4* __restrict__ pos4,
                                                             const double* __restrict__ vel, long long n,

@@ -104,6 +104,9 @@ cudaError_t launch_pack(double4* pos4, const double* x, const double* y, const d
 cudaError_t launch_unpack(const double4* pos4, double* x, double* y, double* z, long long n, cudaStream_t st);
 cudaError_t launch_potential(const DeviceState& s, const StepParams& p, bool faithful_order, double* d_out,
                              cudaStream_t st, int* launches);
+// acc[slab] = sum over ranks of peer_acc[r][slab], rank order (orb_peer_reduce)
+cudaError_t launch_peer_reduce(const double* const* peer_acc, int world, double* acc, long long n, long long lo,
+                               long long hi, cudaStream_t st);
 // potential term of Object.lagrangian (physics.py:275-279) for body i, reference order, unsoftened
 cudaError_t launch_body_potential(const DeviceState& s, long long i, double G, double* d_out, cudaStream_t st);
 cudaError_t launch_energy_angmom(const DeviceState& s, double* d_out4, cudaStream_t st, int* launches);

@@ -67,6 +67,8 @@ def _worker(rank, world, port, backend, n, steps, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group(backend, rank=rank, world_size=world)
     kind = os.path.basename(out_dir)
+    if kind == "fast_nccl":                     # the same run with the partial accelerations summed by NCCL
+        os.environ["ORBITAL_B200_PEER_REDUCE"] = "0"
     c, f32, vel, radius = _scenario(n, kind)
     if backend == "gloo":
         Sys = _fake_sharded_class(torch, partial=(kind == "partial"))
@@ -83,7 +85,8 @@ def _worker(rank, world, port, backend, n, steps, out_dir):
     st = sysm.gather_state()
     K, L = sysm.energy_angmom()
     if rank == 0:
-        np.savez(os.path.join(out_dir, "result.npz"), K=K, L=L, resolved=resolved, **st)
+        np.savez(os.path.join(out_dir, "result.npz"), K=K, L=L, resolved=resolved,
+                 peer=int(bool(getattr(sysm, "_peer", False))), **st)
     dist.barrier()
     sysm.close()
     dist.destroy_process_group()
@@ -182,8 +185,10 @@ def test_engine_over_in_process_ranks_history_and_frames(golden, monkeypatch, tm
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("kind", ["faithful", "fast", "faithful_contacts"])
+@pytest.mark.parametrize("kind", ["faithful", "fast", "fast_nccl", "faithful_contacts"])
 def test_multi_rank_nccl_matches_single_gpu(orc, tmp_path, kind, world):
+    """One process per GPU over NCCL.  kind=fast: the partial accelerations of the pair-symmetric kernel are summed
+    straight out of peer memory (CUDA IPC, orb_peer_reduce); fast_nccl: the same run with NCCL's all-reduce."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs (the same kernels run on one GPU in tests/test_sharded_gpu.py)")
@@ -199,6 +204,8 @@ def test_multi_rank_nccl_matches_single_gpu(orc, tmp_path, kind, world):
             assert np.array_equal(got[k], ref), k
         else:
             assert np.allclose(got[k], ref, rtol=1e-11, atol=0), k
+    if kind.startswith("fast"):
+        assert int(got["peer"]) == (1 if kind == "fast" else 0)
 
 
 @pytest.mark.gpu
