@@ -359,6 +359,9 @@ class ShardedSystem:
 
     def accel(self):
         """Constructor force pass (engine.py:41): no overlap test."""
+        if self._peer:
+            # no position all-gather precedes this force pass: keep it behind everybody's previous peer reduction
+            self.comm.dist.all_reduce(self._peer_flag, group=self.comm.group)
         for d in self.devs:
             d.accel()
         self._reduce_acc()
