@@ -1019,7 +1019,7 @@ int orb_history_download(orb_engine* e, int64_t last_k, double* out, int64_t* go
 // ===========================================================================
 // Ensemble
 // ===========================================================================
-constexpr int kEnsNarrowBelow = 4;      // warps per SM sub-partition below which the fast kernel goes one body per lane
+constexpr int kEnsNarrowBelow = 6;      // warps per SM sub-partition below which the fast kernel goes one body per lane
 
 struct orb_ensemble {
     std::mutex mu;

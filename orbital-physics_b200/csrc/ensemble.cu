@@ -17,6 +17,7 @@
 //             offset s lane I meets the two bodies of lane I+s (positions from shared memory), evaluates the
 //             2x2 pairs, keeps its own accelerations and adds the reactions to a travelling accumulator that
 //             rotates one lane per offset (12 SHFL per 4 pairs) and is sent home after the last offset.
+#include <algorithm>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -501,11 +502,16 @@ __device__ __forceinline__ void ens_fast_body1(const EnsArgs& g, long long sys0,
     }
 }
 
+// ORB_ENS_NARROW_MINB CTAs of 4 warps per SM (register cap 65536 / (128 * MINB))
+constexpr int kEnsNarrowWarps = 4;
+#ifndef ORB_ENS_NARROW_MINB
+#define ORB_ENS_NARROW_MINB 5
+#endif
 template <int NBP, int VM>
-__global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast1_kernel(const EnsArgs g) {
+__global__ void __launch_bounds__(32 * kEnsNarrowWarps, ORB_ENS_NARROW_MINB) ens_step_fast1_kernel(const EnsArgs g) {
     constexpr int SPW = 32 / NBP;                // systems per warp
-    __shared__ double2 sxy_all[kEnsMaxWarps][32];
-    __shared__ double sz_all[kEnsMaxWarps][32];
+    __shared__ double2 sxy_all[kEnsNarrowWarps][32];
+    __shared__ double sz_all[kEnsNarrowWarps][32];
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const long long sys0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * SPW;
@@ -639,6 +645,8 @@ static void launch_ens_variant(const EnsArgs& a, int w, cudaStream_t st) {
         cfg.gridDim = dim3((unsigned)((a.nsys + w - 1) / w));                   // one warp per system
         cudaLaunchKernelEx(&cfg, ens_step_kernel<NBP, VM, DETECT>, a);
     } else if (!DETECT && a.narrow) {
+        w = std::min(w, kEnsNarrowWarps);
+        cfg.blockDim = dim3(32 * w);
         const long long per_cta = (long long)w * (32 / NBP);                    // one body per lane
         cfg.gridDim = dim3((unsigned)((a.nsys + per_cta - 1) / per_cta));
         cudaLaunchKernelEx(&cfg, ens_step_fast1_kernel<NBP, VM>, a);
