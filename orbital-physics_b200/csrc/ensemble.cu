@@ -383,12 +383,15 @@ __device__ __forceinline__ void ens_fast_body(const EnsArgs& g, long long sys0, 
     }
 }
 
+// 4 warps per CTA, 4 CTAs per SM (128 registers): with the resident-CTA hint ptxas schedules ~1 % better than with
+// the bare 256-thread bound (profiles/r2b_ens_narrow.txt)
+constexpr int kEnsFastWarps = 4;
 template <int NBP, int VM, bool DETECT>
-__global__ void __launch_bounds__(32 * kEnsMaxWarps) ens_step_fast_kernel(const EnsArgs g) {
+__global__ void __launch_bounds__(32 * kEnsFastWarps, 4) ens_step_fast_kernel(const EnsArgs g) {
     constexpr int SPW = 64 / NBP;                // systems per warp
     constexpr int SLOTS = SPW * 3 * (NBP / 2);
-    __shared__ double2 sxy_all[kEnsMaxWarps][SLOTS];
-    __shared__ double sz_all[kEnsMaxWarps][SLOTS];
+    __shared__ double2 sxy_all[kEnsFastWarps][SLOTS];
+    __shared__ double sz_all[kEnsFastWarps][SLOTS];
     __shared__ ContactBody cb_all[DETECT ? kEnsDetectWarps : 1][DETECT ? SPW * NBP : 1];
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
@@ -651,6 +654,8 @@ static void launch_ens_variant(const EnsArgs& a, int w, cudaStream_t st) {
         cfg.gridDim = dim3((unsigned)((a.nsys + per_cta - 1) / per_cta));
         cudaLaunchKernelEx(&cfg, ens_step_fast1_kernel<NBP, VM>, a);
     } else {
+        w = std::min(w, kEnsFastWarps);
+        cfg.blockDim = dim3(32 * w);
         const long long per_cta = (long long)w * (64 / NBP);                    // 64/NBP systems per warp
         cfg.gridDim = dim3((unsigned)((a.nsys + per_cta - 1) / per_cta));
         cudaLaunchKernelEx(&cfg, ens_step_fast_kernel<NBP, VM, DETECT>, a);
