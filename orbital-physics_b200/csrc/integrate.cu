@@ -786,7 +786,8 @@ cudaError_t launch_body_potential(const DeviceState& s, long long i, double G, d
 }
 
 // Sum of the ranks' partial accelerations for this rank's slab, read from peer memory (see orb_peer_reduce).
-// Volatile loads: the addresses were read in the previous step too and nothing may be served from a stale line.
+// ld.global.cv: the addresses were read in the previous step too and nothing may be served from a stale line; all
+// peers' loads are issued before the first addition (memory-level parallelism over NVLink).
 struct PeerAcc { const double* p[16]; };
 __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerAcc peers, int world, double* acc, long long n,
                                                           long long lo, long long hi) {
@@ -795,8 +796,14 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerAcc peers, i
     if (t >= 3 * per) return;
     const long long c = t / per;
     const long long idx = c * n + lo + (t - c * per);
+    double v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)             // compile-time index: the pointers stay in the parameter bank
+        v[r] = r < world ? __ldcv(peers.p[r] + idx) : 0.0;
     double s = 0.0;
-    for (int r = 0; r < world; ++r) s += *reinterpret_cast<const volatile double*>(peers.p[r] + idx);   // rank order
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+        if (r < world) s += v[r];            // rank order
     acc[idx] = s;
 }
 
