@@ -600,7 +600,7 @@ def test_ensemble_time_sliced_fused_kernel_is_bit_identical(nat, monkeypatch, nb
 
 @pytest.mark.parametrize("nb", [2, 3, 7, 16, 21, 32])
 def test_ensemble_one_body_per_lane_layout(nat, monkeypatch, nb):
-    """The narrow layout (ens_step_fast1_kernel: one body per lane, what a batch with fewer than 4 warps of work per
+    """The narrow layout (ens_step_fast1_kernel: one body per lane, what a batch with fewer than 6 warps of work per
     SM sub-partition takes by default): fused, one launch per step (incl. the 16-step graphs) and mixed calls give
     the same bits; per-body velocity dtypes; padded slots and the ragged last warp contribute nothing; the
     trajectories stay within 1e-10 of the two-body layout (which other tests hold to the oracle) over 40 steps."""
