@@ -374,6 +374,18 @@ int tiny_limit() {
     return v < 0 ? 0 : (v > kTinyMax ? kTinyMax : v);
 }
 
+// ordered sum of 8 * NB row entries starting from +0.0 (ascending j, physics.py:154)
+template <int NB>
+__device__ __forceinline__ double row_sum_blocks(const double* row) {
+    double v[8 * NB];
+#pragma unroll
+    for (int j = 0; j < 8 * NB; ++j) v[j] = row[j];
+    double b = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8 * NB; ++j) b = __dadd_rn(b, v[j]);
+    return b;
+}
+
 template <bool DETECT>
 __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, double* vel, double* acc,
                                                              const double* __restrict__ radius,
@@ -383,7 +395,8 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
                                                              double restitution, int device_contacts, int stash_u, Ctl* ctl, long long* pairs) {
     if (ctl->halted) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int stride = n | 1;                               // odd row stride: conflict-free column walks
+    const int npad = (n + 7) & ~7;                          // row sums run in whole blocks of 8 (padding: +0.0)
+    const int stride = npad | 1;                            // odd row stride: conflict-free column walks
     double4* sp = reinterpret_cast<double4*>(smem_raw);     // {x,y,z,G*m}
     double* sr = reinterpret_cast<double*>(sp + n);         // radius
     double* T = sr + n;                                     // 3 x n x stride
@@ -423,14 +436,25 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
         f32 = vf32[body] != 0;
         if (comp == 0) sr[body] = radius[body];
         T[comp * plane + body * stride + body] = 0.0;        // diagonal of the three term planes: +0.0
+        for (int j = n; j < npad; ++j) T[comp * plane + body * stride + j] = 0.0;   // and the padding of the row
     }
     double* spq = reinterpret_cast<double*>(sp + body) + comp;       // this thread's slot of sp[body]
     __syncthreads();
     const int first_pair = tid < npairs ? plist[tid] : 0;   // most systems: at most one pair per lane
     const long long hist0 = ctl->hist_count;
     long long slot = hist_cap > 0 ? hist0 % hist_cap : 0;    // ring cursor, advanced without a 64-bit modulo per step
+    const long long hstep = 3LL * n;                          // ... and this thread's slot in it, advanced by addition
+    double* hp = hist_cap > 0 ? hist + (slot * n + body) * 3 + comp : nullptr;
     long long done = 0;
     if (active && comp == 0) sp[body].w = gm;
+    // -DORB_MICRO_PROFILE: cycles per phase and warp, printed at the end of a launch (development aid; build a second
+    // library with `make OUT=... BUILD=... EXTRA=-DORB_MICRO_PROFILE` and point ORBITAL_B200_LIB at it)
+#ifdef ORB_MICRO_PROFILE
+    long long tA = 0, tB = 0, tC = 0, tD = 0, t0 = clock64(), t1;
+#define ORB_MP(acc) { t1 = clock64(); acc += t1 - t0; t0 = t1; }
+#else
+#define ORB_MP(acc)
+#endif
     for (long long s = 0; s < nsteps; ++s) {
         if (active) {
             v = kick_faithful(v, h, a, f32);                         // engine.py:69-70
@@ -438,6 +462,7 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             *spq = q;
         }
         __syncthreads();
+        ORB_MP(tA)
         for (int p = tid; p < npairs; p += blockDim.x) {            // physics.py:136-155, one pair per lane
             const int code = (p == tid) ? first_pair : plist[p];
             const int i = code >> 8, j = code & 0xff;
@@ -460,6 +485,7 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             }
         }
         __syncthreads();
+        ORB_MP(tB)
         // two flags, alternating by step: the one of the next step is cleared while nobody can be setting it
         const int hits = DETECT ? hitflag[s & 1] : 0;
         if (DETECT && tid == 0) hitflag[(s + 1) & 1] = 0;
@@ -468,13 +494,27 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             double b = 0.0;                                          // physics.py:132
             // ascending j.  The diagonal entry holds +0.0: x + 0.0 == x bit for bit because a running sum that
             // starts at +0.0 can never be -0.0, so the self pair is "skipped" without a branch and the
-            // shared-memory loads pipeline freely.
-#pragma unroll 8
-            for (int j = 0; j < n; ++j) b = __dadd_rn(b, row[j]);
+            // shared-memory loads pipeline freely.  The row is padded with +0.0 to a multiple of 8 for the same
+            // reason: whole unrolled blocks, no remainder loop (r2b: clock64 per phase at N = 15 showed this phase at
+            // 610 of the step's 1,900 cycles -- seven branchy remainder iterations around 14 dependent additions).
+            // Up to 32 bodies the whole row is one straight-line block: all loads issue before the first addition, so
+            // the chain pays one shared-memory latency, not one per block of 8 (N = 15: 490 -> 2xx cycles).
+            switch (npad >> 3) {
+                case 1: b = row_sum_blocks<1>(row); break;
+                case 2: b = row_sum_blocks<2>(row); break;
+                case 3: b = row_sum_blocks<3>(row); break;
+                case 4: b = row_sum_blocks<4>(row); break;
+                default:
+                    for (int j0 = 0; j0 < npad; j0 += 8) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) b = __dadd_rn(b, row[j0 + j]);
+                    }
+            }
             a = b;
             v = kick_faithful(v, h, a, f32);                         // engine.py:81-82
         }
         ++done;
+        ORB_MP(tC)
         if (hits) {
             if (!device_contacts) break;                             // the host resolves and resumes
             // engine.py:85: contacts after the second half-kick, resolved here in the reference's order
@@ -500,9 +540,16 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             if (tid == 0) ctl->u_valid = 0;
             u_set = false;
         }
-        if (active && hist_cap > 0) hist[(slot * n + body) * 3 + comp] = q;   // engine.py:88-92
-        if (++slot >= hist_cap) slot = 0;
+        if (active && hist_cap > 0) *hp = q;                                  // engine.py:88-92
+        hp += hstep;
+        if (++slot >= hist_cap) { slot = 0; hp -= hist_cap * hstep; }
+        ORB_MP(tD)
     }
+#ifdef ORB_MICRO_PROFILE
+    if ((tid & 31) == 0 && nsteps >= 100)
+        printf("micro profile warp %d: cycles per step  kick+drift+bar %.0f  pairs+bar %.0f  rowsum+kick %.0f  tail %.0f\n",
+               tid >> 5, (double)tA / nsteps, (double)tB / nsteps, (double)tC / nsteps, (double)tD / nsteps);
+#endif
     if (active) {
         reinterpret_cast<double*>(pos4 + body)[comp] = q;
         vel[body + comp * n] = v;
@@ -526,7 +573,7 @@ static int micro_block(int n) {
 }
 
 static size_t micro_smem(int n) {
-    const int stride = n | 1;
+    const int stride = ((n + 7) & ~7) | 1;
     return (size_t)n * (sizeof(double4) + sizeof(double)) + (size_t)3 * n * stride * sizeof(double) +
            (256 + 4) * sizeof(double) + (size_t)(n * (n - 1) / 2 + 8) * sizeof(unsigned short) + 32;
 }
