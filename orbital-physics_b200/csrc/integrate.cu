@@ -499,16 +499,16 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
             // 610 of the step's 1,900 cycles -- seven branchy remainder iterations around 14 dependent additions).
             // Up to 32 bodies the whole row is one straight-line block: all loads issue before the first addition, so
             // the chain pays one shared-memory latency, not one per block of 8 (N = 15: 490 -> 2xx cycles).
-            switch (npad >> 3) {
-                case 1: b = row_sum_blocks<1>(row); break;
-                case 2: b = row_sum_blocks<2>(row); break;
-                case 3: b = row_sum_blocks<3>(row); break;
-                case 4: b = row_sum_blocks<4>(row); break;
-                default:
-                    for (int j0 = 0; j0 < npad; j0 += 8) {
+            // (uniform compare-and-branch chain: a `switch` becomes a jump table -- constant load + indirect branch)
+            if (npad == 16) b = row_sum_blocks<2>(row);
+            else if (npad == 8) b = row_sum_blocks<1>(row);
+            else if (npad == 24) b = row_sum_blocks<3>(row);
+            else if (npad == 32) b = row_sum_blocks<4>(row);
+            else {
+                for (int j0 = 0; j0 < npad; j0 += 8) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) b = __dadd_rn(b, row[j0 + j]);
-                    }
+                    for (int j = 0; j < 8; ++j) b = __dadd_rn(b, row[j0 + j]);
+                }
             }
             a = b;
             v = kick_faithful(v, h, a, f32);                         // engine.py:81-82
