@@ -441,6 +441,10 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
     double* spq = reinterpret_cast<double*>(sp + body) + comp;       // this thread's slot of sp[body]
     __syncthreads();
     const int first_pair = tid < npairs ? plist[tid] : 0;   // most systems: at most one pair per lane
+    const int fi = first_pair >> 8, fj = first_pair & 0xff;
+    double* const fTi = T + fi * stride + fj;
+    double* const fTj = T + fj * stride + fi;
+    const double fRi = DETECT ? sr[fi] : 0.0, fRj = DETECT ? sr[fj] : 0.0;     // radii do not change inside a launch
     const long long hist0 = ctl->hist_count;
     long long slot = hist_cap > 0 ? hist0 % hist_cap : 0;    // ring cursor, advanced without a 64-bit modulo per step
     const long long hstep = 3LL * n;                          // ... and this thread's slot in it, advanced by addition
@@ -457,32 +461,46 @@ __global__ void __launch_bounds__(256, 1) micro_steps_kernel(double4* pos4, doub
 #endif
     for (long long s = 0; s < nsteps; ++s) {
         if (active) {
-            v = kick_faithful(v, h, a, f32);                         // engine.py:69-70
-            q = drift_faithful(q, v, dt, dt32, f32);                 // engine.py:73-75
+            // kick_faithful + drift_faithful (common.cuh) with the float32 velocity kept from the kick: the drift's
+            // float32(v) is that very value, so one conversion less sits on the step's dependent chain
+            const double r = __dadd_rn(v, __dmul_rn(h, a));          // engine.py:69-70
+            if (f32) {
+                const float vf = __double2float_rn(r);
+                v = (double)vf;
+                q = __dadd_rn(q, (double)__fmul_rn(vf, dt32));       // engine.py:73-75, product in float32
+            } else {
+                v = r;
+                q = __dadd_rn(q, __dmul_rn(v, dt));
+            }
             *spq = q;
         }
         __syncthreads();
         ORB_MP(tA)
-        for (int p = tid; p < npairs; p += blockDim.x) {            // physics.py:136-155, one pair per lane
-            const int code = (p == tid) ? first_pair : plist[p];
-            const int i = code >> 8, j = code & 0xff;
-            const double4 pi = sp[i], pj = sp[j];
+        // physics.py:136-155, one pair per lane: the lane's first pair with everything that does not change between
+        // steps (slots, radii, term addresses) held in registers; further pairs (n > 23 at 256 threads) by index
+        auto pair = [&](const double4* ppi, const double4* ppj, double Ri, double Rj, double* Ti, double* Tj, int i,
+                        int j) {
+            const double4 pi = *ppi, pj = *ppj;
             const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y), dz = __dsub_rn(pj.z, pi.z);  // :145
             // physics.py:517-518 (ri - rj): tested up front so that it overlaps the sqrt / divide chain below
-            const bool touching = DETECT && overlap_exact(-dx, -dy, -dz, sr[i], sr[j]);
+            const bool touching = DETECT && overlap_exact(-dx, -dy, -dz, Ri, Rj);
             const double r2 = __dadd_rn(dot3_numpy(dx, dy, dz), eps2);                                        // :146
             const double inv_r = __ddiv_rn(1.0, __dsqrt_rn(r2));                                              // :147
             const double inv_r3 = __ddiv_rn(inv_r, r2);                                                       // :148
             const double si = __dmul_rn(pj.w, inv_r3);               // (G mj) inv_r3          :151
             const double sj = __dmul_rn(pi.w, inv_r3);               // (G mi) inv_r3          :152 (sign applied below)
-            double* Ti = T + i * stride + j;
-            double* Tj = T + j * stride + i;
             Ti[0] = __dmul_rn(si, dx); Ti[plane] = __dmul_rn(si, dy); Ti[2 * plane] = __dmul_rn(si, dz);
             Tj[0] = -__dmul_rn(sj, dx); Tj[plane] = -__dmul_rn(sj, dy); Tj[2 * plane] = -__dmul_rn(sj, dz);
             if (touching) {
                 record_overlap(ctl, pairs, i, j);
                 hitflag[s & 1] = 1;
             }
+        };
+        if (tid < npairs) pair(sp + fi, sp + fj, fRi, fRj, fTi, fTj, fi, fj);
+        for (int p = tid + blockDim.x; p < npairs; p += blockDim.x) {
+            const int code = plist[p];
+            const int i = code >> 8, j = code & 0xff;
+            pair(sp + i, sp + j, DETECT ? sr[i] : 0.0, DETECT ? sr[j] : 0.0, T + i * stride + j, T + j * stride + i, i, j);
         }
         __syncthreads();
         ORB_MP(tB)
