@@ -540,7 +540,9 @@ class SimulationEngine:
         objs = self.objects.objects
         if len(objs) != len(self._bound) or not all(map(operator.is_, objs, self._bound)):
             return False
-        return (float(self.dt), float(self.softening), float(self._G), float(self.restitution)) == self._params
+        p = self._params                     # (dt, softening, G, restitution) as last sent to the device
+        return (p is not None and self.dt == p[0] and self.softening == p[1] and self._G == p[2]
+                and self.restitution == p[3])
 
     def _prune_watch(self):
         """Stop tracking velocity arrays nobody holds any more: once the caller has dropped the ndarray it got from
